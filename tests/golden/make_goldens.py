@@ -1,0 +1,201 @@
+"""Generate golden vectors by running the UNMODIFIED reference modules on CPU (fp32).
+
+    python tests/golden/make_goldens.py            # needs /root/reference (this container only)
+
+The reference imports fine once `apex.normalization.fused_layer_norm.FusedLayerNorm` is shimmed
+to torch.nn.LayerNorm (the only apex symbol model/*.py uses; same parameter names, same eps
+argument, biased variance, fp32 statistics).  Weights are NOT stored: they are regenerated on
+the test side from `uniter_b200.synth.seeded_state` (per-key seeded), and each golden file
+records a checksum of the weights it was produced with.  Outputs are stored as fp32 .npz.
+
+Cases:
+  tiny_*   H=128, 2 heads, 2 layers, I=512 — every tap, every output, full gradients
+  c1a / c1b  BASELINE config[0]: UNITER-base 1 layer, B=2, 20 txt + 36 regions (and a ragged
+             variant (20,36),(14,30)) — outputs, taps, gradient fingerprints
+  *_adv    adversarial gather_index (permutation inside the valid range and the malformed index
+           of data/itm.py:356-361) — embedding output, bit-exact row selection
+  heads    VQA logits / MLM scores / ITM scores through the reference heads on top of the
+           reference encoder
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = os.environ.get("UNITER_REFERENCE", "/root/reference")
+
+
+def import_reference():
+    apex = types.ModuleType("apex")
+    norm = types.ModuleType("apex.normalization")
+    fln = types.ModuleType("apex.normalization.fused_layer_norm")
+    fln.FusedLayerNorm = torch.nn.LayerNorm
+    apex.normalization = norm
+    norm.fused_layer_norm = fln
+    sys.modules.setdefault("apex", apex)
+    sys.modules.setdefault("apex.normalization", norm)
+    sys.modules.setdefault("apex.normalization.fused_layer_norm", fln)
+    sys.path.insert(0, REF)
+    import model.model as rm            # noqa: E402
+    import model.vqa as rvqa            # noqa: E402
+    import model.pretrain as rpre       # noqa: E402
+    return rm, rvqa, rpre
+
+
+def state_checksum(state):
+    acc = 0.0
+    for k in sorted(state):
+        acc += float(state[k].double().abs().sum()) + 3.0 * float(state[k].double().sum())
+    return np.float64(acc)
+
+
+def grad_fingerprint(g, key):
+    """(l2 norm, sum, 16 sampled entries) — compact stand-in for a full gradient tensor."""
+    import hashlib
+    h = int(hashlib.sha1(key.encode()).hexdigest()[:8], 16)
+    gen = torch.Generator().manual_seed(h & 0x7FFFFFFF)
+    flat = g.reshape(-1).double()
+    idx = torch.randint(0, flat.numel(), (16,), generator=gen)
+    return np.concatenate([[flat.norm().item(), flat.sum().item()], flat[idx].numpy()])
+
+
+def run_case(rm, cfg_kw, img_dim, batch, out_path, full_grads, seed=0, adversarial=None):
+    from uniter_b200.synth import seeded_state
+    cfg = rm.UniterConfig(**cfg_kw)
+    model = rm.UniterModel(cfg, img_dim)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    state = seeded_state(shapes, seed=seed)
+    model.load_state_dict(state, strict=True)
+    model.eval()  # dropout off: parity is only defined at p = 0
+
+    gi = batch["gather_index"]
+    if adversarial == "perm":
+        g = torch.Generator().manual_seed(99)
+        gi = gi.clone()
+        for b in range(gi.size(0)):
+            n = int(batch["attn_masks"][b].sum())
+            gi[b, :n] = gi[b, :n][torch.randperm(n, generator=g)]
+    elif adversarial == "malformed":
+        # data/itm.py:356-361 passes a stale max_len: image slots index text-padding rows
+        from uniter_b200.synth import get_gather_index
+        Lt = batch["input_ids"].size(1)
+        gi = get_gather_index(batch["txt_lens"], batch["num_bbs"], gi.size(0),
+                              min(batch["txt_lens"]), gi.size(1))
+        gi = gi.clamp(max=Lt + batch["img_feat"].size(1) - 1)
+
+    taps = {}
+    l0 = model.encoder.layer[0]
+    hooks = [
+        l0.attention.self.register_forward_hook(lambda m, i, o: taps.__setitem__("ctx", o.detach())),
+        l0.attention.register_forward_hook(lambda m, i, o: taps.__setitem__("attn_out", o.detach())),
+        l0.intermediate.register_forward_hook(lambda m, i, o: taps.__setitem__("ffn1", o.detach())),
+        l0.register_forward_hook(lambda m, i, o: taps.__setitem__("layer_out", o.detach())),
+    ]
+    emb = model._compute_img_txt_embeddings(batch["input_ids"], batch["position_ids"],
+                                            batch["img_feat"], batch["img_pos_feat"], gi)
+    outs = model(batch["input_ids"], batch["position_ids"], batch["img_feat"],
+                 batch["img_pos_feat"], batch["attn_masks"], gi, output_all_encoded_layers=True)
+    for h in hooks:
+        h.remove()
+    pooled = model.pooler(outs[-1])
+    maskf = batch["attn_masks"].float()
+    loss = ((outs[-1] * maskf[..., None]) ** 2).sum() / maskf.sum() / outs[-1].size(-1)
+    model.zero_grad()
+    loss.backward()
+
+    rec = {
+        "weights_checksum": state_checksum(state),
+        "gather_index": gi.numpy(),
+        "embedding_output": emb.detach().numpy(),
+        "pooled": pooled.detach().numpy(),
+        "loss": np.float64(loss.item()),
+    }
+    for i, o in enumerate(outs):
+        rec["layer_%d" % i] = o.detach().numpy()
+    for k, v in taps.items():
+        if k == "ffn1" and not full_grads:
+            continue  # [B, L, 3072] is big; kept only for the tiny case
+        rec["tap_" + k] = v.numpy()
+    for name, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        if full_grads:
+            rec["grad/" + name] = p.grad.numpy()
+        rec["gfp/" + name] = grad_fingerprint(p.grad, name)
+    np.savez_compressed(out_path, **rec)
+    print("wrote", out_path, "%.1f KB" % (os.path.getsize(out_path) / 1024), "loss", loss.item())
+    return model, state
+
+
+def run_heads(rm, rvqa, rpre, out_path):
+    """Head-level logits through the reference heads + reference encoder (tiny config)."""
+    from uniter_b200.synth import seeded_state, synth_batch
+    cfg_kw = TINY
+    img_dim = 64
+    batch = synth_batch(3, 5, 9, 4, 8, seed=7, img_dim=img_dim, vocab_size=cfg_kw["vocab_size_or_config_json_file"],
+                        mlm_prob=0.3)
+    rec = {}
+    # --- VQA
+    cfg = rm.UniterConfig(**cfg_kw)
+    vqa = rvqa.UniterForVisualQuestionAnswering(cfg, img_dim, 17)
+    st = seeded_state({k: tuple(v.shape) for k, v in vqa.state_dict().items()}, seed=3)
+    vqa.load_state_dict(st, strict=True)
+    vqa.eval()
+    b = dict(batch)
+    b["targets"] = torch.rand(3, 17, generator=torch.Generator().manual_seed(5))
+    logits = vqa(b, compute_loss=False)
+    rec["vqa_logits"] = logits.detach().numpy()
+    rec["vqa_checksum"] = state_checksum(st)
+    # --- pretraining heads (MLM, ITM)
+    pre = rpre.UniterForPretraining(cfg, img_dim, 11)
+    st = seeded_state({k: tuple(v.shape) for k, v in pre.state_dict().items()}, seed=4)
+    pre.load_state_dict(st, strict=True)
+    pre.eval()
+    scores = pre(batch, task="mlm", compute_loss=False)
+    rec["mlm_scores"] = scores.detach().numpy()
+    b = dict(batch)
+    b["targets"] = torch.tensor([1, 0, 1])
+    b["ot_inputs"] = None
+    itm, _ = pre(b, task="itm", compute_loss=False)
+    rec["itm_scores"] = itm.detach().numpy()
+    rec["pre_checksum"] = state_checksum(st)
+    np.savez_compressed(out_path, **rec)
+    print("wrote", out_path, "%.1f KB" % (os.path.getsize(out_path) / 1024))
+
+
+TINY = dict(vocab_size_or_config_json_file=2000, hidden_size=128, num_hidden_layers=2,
+            num_attention_heads=2, intermediate_size=512, hidden_act="gelu",
+            hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1,
+            max_position_embeddings=64, type_vocab_size=2, initializer_range=0.02)
+BASE_L1 = dict(vocab_size_or_config_json_file=28996, hidden_size=768, num_hidden_layers=1,
+               num_attention_heads=12, intermediate_size=3072, hidden_act="gelu",
+               hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1,
+               max_position_embeddings=512, type_vocab_size=2, initializer_range=0.02)
+
+
+def main():
+    from uniter_b200.synth import synth_batch
+    rm, rvqa, rpre = import_reference()
+    torch.set_num_threads(8)
+    # tiny: ragged batch of 4
+    tb = synth_batch(4, 5, 12, 3, 9, seed=11, img_dim=64, vocab_size=2000)
+    run_case(rm, TINY, 64, tb, os.path.join(HERE, "tiny.npz"), full_grads=True)
+    run_case(rm, TINY, 64, tb, os.path.join(HERE, "tiny_adv_perm.npz"), full_grads=False,
+             adversarial="perm")
+    run_case(rm, TINY, 64, tb, os.path.join(HERE, "tiny_adv_malformed.npz"), full_grads=False,
+             adversarial="malformed")
+    # C1a: no padding; C1b: ragged
+    c1a = synth_batch(2, 0, 0, 0, 0, seed=0, txt_lens=[20, 20], num_bbs=[36, 36])
+    run_case(rm, BASE_L1, 2048, c1a, os.path.join(HERE, "c1a.npz"), full_grads=False)
+    c1b = synth_batch(2, 0, 0, 0, 0, seed=0, txt_lens=[20, 14], num_bbs=[36, 30])
+    run_case(rm, BASE_L1, 2048, c1b, os.path.join(HERE, "c1b.npz"), full_grads=False)
+    run_heads(rm, rvqa, rpre, os.path.join(HERE, "heads_tiny.npz"))
+
+
+if __name__ == "__main__":
+    main()

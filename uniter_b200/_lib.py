@@ -1,0 +1,75 @@
+"""ctypes binding of libub200.so — the only way Python reaches the CUDA kernels.
+
+There is deliberately no fallback: if the library is missing or the device is not sm_100 the
+import of the compute path raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libub200.so")
+
+F16, BF16 = 0, 1
+EPI_BIAS, EPI_DROPOUT, EPI_RESIDUAL, EPI_GELU = 1, 2, 4, 8
+EPI_DGELU, EPI_ACCUM, EPI_OUT_F32, EPI_COLSUM = 16, 32, 64, 128
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("b", C.c_void_p),
+        ("lda", C.c_int64), ("ldb", C.c_int64),
+        ("a_major", C.c_int32), ("b_major", C.c_int32),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("dtype", C.c_int32), ("epilogue", C.c_int32),
+        ("bias", C.c_void_p), ("residual", C.c_void_p), ("aux", C.c_void_p),
+        ("out", C.c_void_p), ("out2", C.c_void_p), ("colsum", C.c_void_p),
+        ("ldr", C.c_int64), ("ldaux", C.c_int64), ("ldo", C.c_int64),
+        ("dropout_p", C.c_float),
+        ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64),
+        ("tile_n", C.c_int32), ("max_ctas", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Load libub200.so (building is the job of ``uniter_b200.build`` / ``__graft_entry__``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libub200.so not found at %s — run `python -m uniter_b200.build` "
+            "(there is no non-CUDA fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.ub200_version.restype = C.c_int
+    lib.ub200_last_error_string.restype = C.c_char_p
+    lib.ub200_device_check.restype = C.c_int
+    lib.ub200_gemm.restype = C.c_int
+    lib.ub200_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("libub200 error %d: %s" % (rc, load().ub200_last_error_string().decode()))
+
+
+def dtype_code(t):
+    import torch
+    if t == torch.bfloat16:
+        return BF16
+    if t == torch.float16:
+        return F16
+    raise TypeError("libub200 computes in fp16 or bf16, got %s" % t)
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def current_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,33 @@
+// Host-side shared helpers: error reporting across the C ABI, TMA descriptor encoding through
+// the driver entry point (no link-time dependency on libcuda, so the library loads on a
+// CPU-only box), device properties cache.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ub200.h"
+
+namespace ub {
+
+int set_error(int code, const char* fmt, ...);  // stores message, returns code
+#define UB_CHECK_ARG(cond, ...)                                    \
+  do {                                                             \
+    if (!(cond)) return ::ub::set_error(UB200_EINVAL, __VA_ARGS__); \
+  } while (0)
+#define UB_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return ::ub::set_error(UB200_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                             __FILE__, __LINE__);                                             \
+  } while (0)
+
+int num_sms();  // SM count of the current device (cached)
+
+// 2-D row-major tensor [rows, cols] of 16-bit elements with row pitch `ld` (elements);
+// box = box_cols x box_rows, 128-byte swizzle, zero OOB fill.  Returns 0 / negative code.
+int make_tma_2d(CUtensorMap* out, const void* base, int dtype, uint64_t rows, uint64_t cols,
+                uint64_t ld, uint32_t box_rows, uint32_t box_cols);
+
+}  // namespace ub

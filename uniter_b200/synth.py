@@ -1,0 +1,127 @@
+"""Seeded synthetic batches and weights in the reference's batch-dict schema.
+
+The reference's collate functions (data/vqa.py:44-71, data/mlm.py:96-136, data/itm.py:282-369)
+emit padded tensors plus a `gather_index`; BASELINE configs use synthetic data of that shape.
+Everything here is CPU torch with an explicit Generator, so the same call yields the same
+batch in the golden generator, the tests, smoke() and bench.py.
+"""
+import hashlib
+
+import torch
+
+
+def get_gather_index(txt_lens, num_bbs, batch_size, max_len, out_size):
+    """Compaction index with the semantics of data/data.py:271-279: slot j of sample i reads
+    text row j for j < tl, image row (j - tl) (stored after the max_len text rows) for
+    tl <= j < tl + nbb, and itself (a padding row) otherwise."""
+    gi = torch.arange(out_size, dtype=torch.long).repeat(batch_size, 1)
+    for i in range(batch_size):
+        tl, nbb = int(txt_lens[i]), int(num_bbs[i])
+        gi[i, tl:tl + nbb] = max_len + torch.arange(nbb, dtype=torch.long)
+    return gi
+
+
+def synth_batch(batch_size, tl_lo, tl_hi, nbb_lo, nbb_hi, seed, img_dim=2048, vocab_size=28996,
+                txt_lens=None, num_bbs=None, mlm_prob=0.0):
+    """One padded batch dict.  Lengths ~ U{lo..hi} unless given explicitly."""
+    g = torch.Generator().manual_seed(seed)
+    if txt_lens is None:
+        txt_lens = torch.randint(tl_lo, tl_hi + 1, (batch_size,), generator=g).tolist()
+    if num_bbs is None:
+        num_bbs = torch.randint(nbb_lo, nbb_hi + 1, (batch_size,), generator=g).tolist()
+    Lt, Li = max(txt_lens), max(num_bbs)
+    L = max(t + n for t, n in zip(txt_lens, num_bbs))
+    input_ids = torch.zeros(batch_size, Lt, dtype=torch.long)
+    img_feat = torch.zeros(batch_size, Li, img_dim)
+    img_pos_feat = torch.zeros(batch_size, Li, 7)
+    attn_masks = torch.zeros(batch_size, L, dtype=torch.long)
+    txt_labels = torch.full((batch_size, Lt), -1, dtype=torch.long)
+    lo_id = min(1000, vocab_size - 1)
+    for i, (tl, nbb) in enumerate(zip(txt_lens, num_bbs)):
+        ids = torch.randint(lo_id, vocab_size, (tl,), generator=g)
+        ids[0] = 101 % vocab_size    # [CLS]
+        ids[-1] = 102 % vocab_size   # [SEP]
+        input_ids[i, :tl] = ids
+        img_feat[i, :nbb] = torch.randn(nbb, img_dim, generator=g)
+        xy = torch.rand(nbb, 4, generator=g)
+        x1 = torch.minimum(xy[:, 0], xy[:, 2]); x2 = torch.maximum(xy[:, 0], xy[:, 2])
+        y1 = torch.minimum(xy[:, 1], xy[:, 3]); y2 = torch.maximum(xy[:, 1], xy[:, 3])
+        w, h = x2 - x1, y2 - y1
+        img_pos_feat[i, :nbb] = torch.stack([x1, y1, x2, y2, w, h, w * h], 1)
+        attn_masks[i, :tl + nbb] = 1
+        if mlm_prob > 0 and tl > 2:
+            m = torch.rand(tl, generator=g) < mlm_prob
+            m[0] = False; m[-1] = False
+            if not m.any():
+                m[1] = True
+            txt_labels[i, :tl][m] = ids[m]
+    batch = {
+        "input_ids": input_ids,
+        "position_ids": torch.arange(Lt, dtype=torch.long).unsqueeze(0),
+        "img_feat": img_feat,
+        "img_pos_feat": img_pos_feat,
+        "attn_masks": attn_masks,
+        "gather_index": get_gather_index(txt_lens, num_bbs, batch_size, Lt, L),
+        "txt_lens": txt_lens,
+        "num_bbs": num_bbs,
+    }
+    if mlm_prob > 0:
+        batch["txt_labels"] = txt_labels
+    return batch
+
+
+def seeded_state(shapes, seed=0, perturb=True):
+    """Deterministic fp32 weights for a {key: shape} schema, independent of module construction
+    order: each tensor is drawn from its own Generator seeded by sha1(key) ^ seed.
+    Linear / Embedding weights ~ N(0, 0.02) (model/model.py:136-141); with `perturb`, biases
+    ~ N(0, 0.02) and LayerNorm weights ~ 1 + N(0, 0.1) so that bias / affine bugs cannot hide
+    behind the reference's zero / one initialisation."""
+    state = {}
+    for key in sorted(shapes):
+        h = int(hashlib.sha1(key.encode()).hexdigest()[:8], 16)
+        g = torch.Generator().manual_seed((h ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
+        shape = tuple(shapes[key])
+        is_ln = "LayerNorm" in key or "layer_norm" in key
+        if key.endswith("bias"):
+            t = torch.randn(shape, generator=g) * 0.02 if perturb else torch.zeros(shape)
+        elif is_ln:
+            t = 1.0 + (torch.randn(shape, generator=g) * 0.1 if perturb else torch.zeros(shape))
+        else:
+            t = torch.randn(shape, generator=g) * 0.02
+        state[key] = t
+    return state
+
+
+def uniter_state_shapes(hidden, layers, inter, vocab, max_pos, type_vocab, img_dim):
+    """State-dict schema of the reference UniterModel (verified against
+    model/model.py:217-304 and model/layer.py:53-185 by tests/golden/make_goldens.py)."""
+    H, I = hidden, inter
+    s = {
+        "embeddings.word_embeddings.weight": (vocab, H),
+        "embeddings.position_embeddings.weight": (max_pos, H),
+        "embeddings.token_type_embeddings.weight": (type_vocab, H),
+        "embeddings.LayerNorm.weight": (H,), "embeddings.LayerNorm.bias": (H,),
+        "img_embeddings.img_linear.weight": (H, img_dim), "img_embeddings.img_linear.bias": (H,),
+        "img_embeddings.img_layer_norm.weight": (H,), "img_embeddings.img_layer_norm.bias": (H,),
+        "img_embeddings.pos_layer_norm.weight": (H,), "img_embeddings.pos_layer_norm.bias": (H,),
+        "img_embeddings.pos_linear.weight": (H, 7), "img_embeddings.pos_linear.bias": (H,),
+        "img_embeddings.mask_embedding.weight": (2, img_dim),
+        "img_embeddings.LayerNorm.weight": (H,), "img_embeddings.LayerNorm.bias": (H,),
+        "pooler.dense.weight": (H, H), "pooler.dense.bias": (H,),
+    }
+    for i in range(layers):
+        p = "encoder.layer.%d." % i
+        for n in ("query", "key", "value"):
+            s[p + "attention.self.%s.weight" % n] = (H, H)
+            s[p + "attention.self.%s.bias" % n] = (H,)
+        s[p + "attention.output.dense.weight"] = (H, H)
+        s[p + "attention.output.dense.bias"] = (H,)
+        s[p + "attention.output.LayerNorm.weight"] = (H,)
+        s[p + "attention.output.LayerNorm.bias"] = (H,)
+        s[p + "intermediate.dense.weight"] = (I, H)
+        s[p + "intermediate.dense.bias"] = (I,)
+        s[p + "output.dense.weight"] = (H, I)
+        s[p + "output.dense.bias"] = (H,)
+        s[p + "output.LayerNorm.weight"] = (H,)
+        s[p + "output.LayerNorm.bias"] = (H,)
+    return s
