@@ -101,6 +101,134 @@ typedef struct {
 
 int ub200_gemm(const ub200_gemm_args* args, ub200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused variable-length multi-head self-attention (head_dim 64), forward and backward.
+ *
+ * Replaces model/layer.py:80-100 (transpose_for_scores, QK^T, /sqrt(d), +mask, softmax, dropout,
+ * PV, permute+contiguous) and its autograd mirror.  `qkv` is the packed [T, 3H] output of the
+ * fused query|key|value projection; sequence b owns rows cu_seqlens[b] .. cu_seqlens[b+1] and
+ * only attends inside that range (the reference's additive -10000 key mask underflows to a
+ * probability of exactly 0, so omitting masked keys is exact).  ctx is [T, H]; lse is
+ * [num_heads, T] fp32 (log-sum-exp of the scaled scores, saved for backward).
+ * Backward reads qkv, ctx, lse, dctx and writes dqkv [T, 3H]; sequences longer than 128 tokens
+ * need `workspace` of ub200_attn_bwd_workspace_bytes() bytes.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* qkv;            /* [T, 3H] 16-bit */
+  void* ctx;                  /* [T, H] 16-bit (output of fwd, input of bwd) */
+  float* lse;                 /* [num_heads, T] */
+  const int32_t* cu_seqlens;  /* [batch + 1], device */
+  int32_t batch, total_tokens, max_seqlen, hidden, num_heads, dtype;
+  float dropout_p;            /* attention_probs_dropout_prob when training, else 0 */
+  uint64_t rng_seed, rng_stream;
+  const void* dctx;           /* bwd: [T, H] */
+  void* dqkv;                 /* bwd: [T, 3H] */
+  void* workspace;            /* bwd: fp32 dQ accumulator or NULL */
+} ub200_attn_args;
+
+int ub200_attn_fwd(const ub200_attn_args* args, ub200_stream_t stream);
+int ub200_attn_bwd(const ub200_attn_args* args, ub200_stream_t stream);
+int64_t ub200_attn_bwd_workspace_bytes(int32_t total_tokens, int32_t hidden, int32_t max_seqlen);
+
+/* ------------------------------------------------------------------------------------------
+ * Row-wise kernels (HBM-bound, 16-byte vector accesses, fp32 statistics).
+ *
+ * ub200_layernorm_fwd / _bwd replace apex FusedLayerNorm(eps=1e-12) at model/layer.py:108,114,
+ * 149,155 and model/model.py:228,243,254-259,270 (biased variance, eps inside the sqrt).  The
+ * backward also produces, in the same pass, dgamma / dbeta, the dropout-masked copy of dx that
+ * feeds the preceding Linear's dgrad / wgrad (dropout at model/layer.py:113,154 regenerated from
+ * the Philox stream used by the forward GEMM epilogue) and that Linear's bias gradient.
+ * ub200_gather_rows is the bit-exact row mover behind pack / unpack and the gather_index
+ * compaction of model/model.py:330-333:  dst[r] = index[r] >= 0 ? src[index[r]] : 0.
+ * ------------------------------------------------------------------------------------------ */
+int ub200_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int32_t rows,
+                        int32_t hidden, int32_t dtype, ub200_stream_t stream);
+
+typedef struct {
+  const void* dy;     /* [rows, hidden] */
+  const void* x;      /* [rows, hidden] input of the forward LayerNorm (pre-LN residual sum) */
+  const void* gamma;  /* [hidden] */
+  void* dx;           /* [rows, hidden] */
+  void* dx_drop;      /* [rows, hidden] dx * mask / keep, required iff dropout_p > 0 */
+  float* dgamma;      /* [hidden] fp32, accumulated */
+  float* dbeta;       /* [hidden] fp32, accumulated */
+  float* dbias;       /* [hidden] fp32 column sum of the Linear-branch gradient, or NULL */
+  int32_t rows, hidden, dtype;
+  float dropout_p;
+  uint64_t rng_seed, rng_stream;
+} ub200_ln_bwd_args;
+int ub200_layernorm_bwd(const ub200_ln_bwd_args* args, ub200_stream_t stream);
+
+int ub200_gather_rows(const void* src, void* dst, const int32_t* index, int32_t rows,
+                      int32_t row_bytes, ub200_stream_t stream);
+int ub200_colsum(const void* x, float* out, int32_t rows, int32_t cols, int64_t ld, int32_t dtype,
+                 ub200_stream_t stream);
+int ub200_cvt_from_f32(const float* src, void* dst, int64_t n, int32_t accumulate, int32_t dtype,
+                       ub200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole encoder stack: NL x BertLayer forward / backward in ONE call each, so that the host
+ * enqueues ~7 (fwd) / ~13 (bwd) kernels per layer from C++ without returning to Python.
+ *
+ * Replaces UniterEncoder.forward (model/model.py:282-292) = NL x BertLayer.forward
+ * (model/layer.py:166-170): BertSelfAttention (:75-101), BertSelfOutput (:111-115),
+ * BertIntermediate (:139-142), BertOutput (:152-156), and the autograd graph behind them.
+ *
+ * Per layer (x = previous layer output, packed [T, H]):
+ *   qkv = x Wqkv^T + bqkv                              GEMM, bias epilogue
+ *   ctx = attention(qkv)                               fused varlen attention
+ *   s1  = dropout(ctx Wo^T + bo) + x                   GEMM, bias + dropout + residual epilogue
+ *   a   = LayerNorm(s1)
+ *   pre = a W1^T + b1 ; f = gelu_erf(pre)              GEMM, bias + GELU epilogue (both kept)
+ *   s2  = dropout(f W2^T + b2) + a                     GEMM, bias + dropout + residual epilogue
+ *   out = LayerNorm(s2)
+ * Weights stay where the nn.Parameters live; query/key/value must be stacked contiguously
+ * ([3H, H] and [3H]) — the Python module guarantees that by making the three parameters views
+ * of one buffer.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void *wqkv, *bqkv;    /* [3H, H], [3H]   attention.self.{query,key,value} stacked */
+  const void *wo, *bo;        /* [H, H], [H]     attention.output.dense */
+  const void *ln1_g, *ln1_b;  /* [H]             attention.output.LayerNorm */
+  const void *w1, *b1;        /* [I, H], [I]     intermediate.dense */
+  const void *w2, *b2;        /* [H, I], [H]     output.dense */
+  const void *ln2_g, *ln2_b;  /* [H]             output.LayerNorm */
+} ub200_layer_weights;
+
+typedef struct {
+  void *dwqkv, *dwo, *dw1, *dw2; /* 16-bit, same shapes as the weights */
+  float* small;                  /* fp32, ub200_encoder_small_grad_count() entries, accumulated:
+                                    dbqkv[3H] dbo[H] dln1_g[H] dln1_b[H] db1[I] db2[H] dln2_g[H] dln2_b[H] */
+} ub200_layer_grads;
+
+typedef struct {
+  int32_t hidden, intermediate, num_heads, num_layers, dtype;
+  int32_t batch, total_tokens, max_seqlen;
+  const int32_t* cu_seqlens;     /* device, [batch + 1] */
+  float hidden_dropout_p;        /* 0 when not training */
+  float attn_dropout_p;
+  uint64_t rng_seed, rng_offset; /* rng_offset must differ between forward calls */
+} ub200_encoder_desc;
+
+/* bytes of saved activations per layer (fwd writes, bwd reads) and of backward scratch */
+int64_t ub200_encoder_act_bytes_per_layer(const ub200_encoder_desc* d);
+int64_t ub200_encoder_bwd_scratch_bytes(const ub200_encoder_desc* d);
+int64_t ub200_encoder_small_grad_count(int32_t hidden, int32_t intermediate);
+
+/* x_in [T, H]; layer_out[l] -> [T, H] output of layer l (caller-allocated, NL pointers);
+ * act: NL * act_bytes_per_layer when save_for_backward, else one layer's worth (reused). */
+int ub200_encoder_fwd(const ub200_encoder_desc* d, const ub200_layer_weights* layers,
+                      const void* x_in, void* const* layer_out, void* act,
+                      int32_t save_for_backward, ub200_stream_t stream);
+
+/* d_layer_out[l]: gradient wrt layer_out[l] or NULL (at least the last must be given);
+ * dx_in [T, H] receives the gradient wrt x_in; accumulate_wgrad != 0 adds into dW*. */
+int ub200_encoder_bwd(const ub200_encoder_desc* d, const ub200_layer_weights* layers,
+                      const ub200_layer_grads* grads, const void* x_in,
+                      void* const* layer_out, const void* act, const void* const* d_layer_out,
+                      void* dx_in, void* scratch, int32_t accumulate_wgrad,
+                      ub200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,94 @@
+"""GPU: tcgen05 GEMM core vs a plain torch fp32 reference of the same op (floating-point kernel:
+tolerance = a few ulps of the 16-bit output type, stated per dtype)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.bfloat16: 2e-2, torch.float16: 4e-3}   # relative to max|ref| (>= 1)
+
+
+def _close(got, ref, tol, what):
+    err = (got.float() - ref).abs().max().item()
+    lim = tol * max(1.0, ref.abs().max().item())
+    assert err <= lim, "%s: max err %.4e > %.4e" % (what, err, lim)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (333, 768, 768), (3451, 2304, 768), (777, 768, 3072),
+                                   (1, 64, 64), (130, 8, 72)])
+@pytest.mark.parametrize("tn", [0, 64, 128, 256])
+def test_gemm_operand_majors(dtype, shape, tn):
+    from uniter_b200 import ops
+    M, N, K = shape
+    torch.manual_seed(M * 7 + N)
+    x = torch.randn(M, K, device="cuda").to(dtype)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(dtype)
+    ref = x.float() @ w.float().t()
+    _close(ops.gemm(x, w, tile_n=tn), ref, TOL[dtype], "K-major x K-major")
+    wt = w.t().contiguous()
+    _close(ops.gemm(x, wt, b_major=1, tile_n=tn), ref, TOL[dtype], "K-major x MN-major (dgrad form)")
+    Mp = (M + 7) // 8 * 8
+    xt = torch.zeros(K, Mp, device="cuda", dtype=dtype)[:, :M]
+    xt.copy_(x.t())
+    _close(ops.gemm(xt, wt, a_major=1, b_major=1, tile_n=tn), ref, TOL[dtype],
+           "MN-major x MN-major (wgrad form)")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_gemm_epilogues(dtype):
+    from uniter_b200 import ops
+    tol = TOL[dtype]
+    torch.manual_seed(1)
+    M, N, K = 515, 768, 768
+    x = torch.randn(M, K, device="cuda").to(dtype)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(dtype)
+    bias = torch.randn(N, device="cuda").to(dtype)
+    res = torch.randn(M, N, device="cuda").to(dtype)
+    base = x.float() @ w.float().t()
+    _close(ops.gemm(x, w, bias=bias), base + bias.float(), tol, "bias")
+    _close(ops.gemm(x, w, bias=bias, residual=res), base + bias.float() + res.float(), tol, "bias+res")
+    out, pre = ops.gemm(x, w, bias=bias, gelu=True)
+    _close(pre, base + bias.float(), tol, "pre-activation")
+    _close(out, torch.nn.functional.gelu(base + bias.float()), tol, "erf gelu")
+    aux = torch.randn(M, N, device="cuda").to(dtype)
+    a32 = aux.float().requires_grad_(True)
+    torch.nn.functional.gelu(a32).sum().backward()
+    _close(ops.gemm(x, w, aux=aux, dgelu=True), base * a32.grad, tol, "dgelu")
+    cs = torch.zeros(N, device="cuda")
+    ops.gemm(x, w, bias=bias, colsum=cs)
+    _close(cs[None], (base + bias.float()).sum(0)[None], 1e-4, "colsum")
+    acc = torch.randn(M, N, device="cuda")
+    acc0 = acc.clone()
+    ops.gemm(x, w, out=acc, accumulate=True)
+    _close(acc, base + acc0, 1e-5, "fp32 accumulate")
+    acc = torch.randn(M, N, device="cuda").to(dtype)
+    acc0 = acc.clone()
+    ops.gemm(x, w, out=acc, accumulate=True)
+    _close(acc, base + acc0.float(), tol, "16-bit accumulate")
+
+
+def test_gemm_dropout_is_deterministic_and_unbiased():
+    from uniter_b200 import ops
+    torch.manual_seed(2)
+    M, N, K = 1024, 768, 256
+    x = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    a = ops.gemm(x, w, dropout_p=0.1, rng_seed=5, rng_stream=1)
+    b = ops.gemm(x, w, dropout_p=0.1, rng_seed=5, rng_stream=1)
+    c = ops.gemm(x, w, dropout_p=0.1, rng_seed=5, rng_stream=2)
+    assert torch.equal(a, b)
+    assert (a != c).float().mean().item() > 0.1
+    frac = (a == 0).float().mean().item()
+    assert abs(frac - 0.1) < 5e-3, frac
+    ref = (x.float() @ w.float().t()) / 0.9
+    kept = a != 0
+    assert ((a.float() - ref).abs() * kept).max().item() < 0.05
+
+
+def test_gemm_rejects_bad_arguments():
+    from uniter_b200 import ops
+    x = torch.randn(16, 60, device="cuda").bfloat16()   # pitch 60 is not a multiple of 8
+    w = torch.randn(16, 60, device="cuda").bfloat16()
+    with pytest.raises(RuntimeError):
+        ops.gemm(x, w)

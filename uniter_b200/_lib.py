@@ -30,6 +30,25 @@ class GemmArgs(C.Structure):
     ]
 
 
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("qkv", C.c_void_p), ("ctx", C.c_void_p), ("lse", C.c_void_p), ("cu_seqlens", C.c_void_p),
+        ("batch", C.c_int32), ("total_tokens", C.c_int32), ("max_seqlen", C.c_int32),
+        ("hidden", C.c_int32), ("num_heads", C.c_int32), ("dtype", C.c_int32),
+        ("dropout_p", C.c_float), ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64),
+        ("dctx", C.c_void_p), ("dqkv", C.c_void_p), ("workspace", C.c_void_p),
+    ]
+
+
+class LnBwdArgs(C.Structure):
+    _fields_ = [
+        ("dy", C.c_void_p), ("x", C.c_void_p), ("gamma", C.c_void_p), ("dx", C.c_void_p),
+        ("dx_drop", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("dbias", C.c_void_p),
+        ("rows", C.c_int32), ("hidden", C.c_int32), ("dtype", C.c_int32),
+        ("dropout_p", C.c_float), ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64),
+    ]
+
+
 _lib = None
 
 
@@ -48,6 +67,19 @@ def load():
     lib.ub200_device_check.restype = C.c_int
     lib.ub200_gemm.restype = C.c_int
     lib.ub200_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+    for name in ("ub200_attn_fwd", "ub200_attn_bwd"):
+        getattr(lib, name).restype = C.c_int
+        getattr(lib, name).argtypes = [C.POINTER(AttnArgs), C.c_void_p]
+    lib.ub200_attn_bwd_workspace_bytes.restype = C.c_int64
+    lib.ub200_attn_bwd_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    lib.ub200_layernorm_fwd.restype = C.c_int
+    lib.ub200_layernorm_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                        C.c_int32, C.c_int32, C.c_void_p]
+    lib.ub200_layernorm_bwd.restype = C.c_int
+    lib.ub200_layernorm_bwd.argtypes = [C.POINTER(LnBwdArgs), C.c_void_p]
+    lib.ub200_colsum.restype = C.c_int
+    lib.ub200_colsum.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32,
+                                 C.c_void_p]
     _lib = lib
     return lib
 

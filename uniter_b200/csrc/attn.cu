@@ -1,0 +1,667 @@
+// Fused variable-length multi-head self-attention for sm_100a (head_dim = 64).
+//
+// Replaces model/layer.py:80-100 of the reference (transpose_for_scores, QK^T, /sqrt(d), +mask,
+// softmax, dropout, PV, permute+contiguous: ~10 launches over the padded [B,h,L,L] rectangle)
+// with ONE kernel over the packed [T, 3H] QKV matrix:
+//   * one CTA per (128-query tile, head, sequence); Q/K/V tiles are TMA'd straight out of the
+//     packed QKV buffer (column offsets 0 / H / 2H select q / k / v, +64*head selects the head);
+//   * S = Q K^T and O = P V run on tcgen05 (M=128, fp32 accumulators in TMEM);
+//   * mask-by-omission: only the S_b valid keys of the sequence take part (the reference's
+//     additive -10000 underflows to exactly 0 probability, so this is exact — SURVEY.md §8a E4);
+//   * softmax in registers, one query row per thread (TMEM lane == row), exp2 with 1/sqrt(d)
+//     folded in; probabilities are normalised and rounded to 16 bit BEFORE P.V, as the
+//     reference's fp16 softmax output is;
+//   * Philox dropout on P regenerated (not stored) by the backward kernel;
+//   * ctx is written directly in [T, H] layout; the row-wise log-sum-exp is saved for backward.
+//
+// Backward (autograd mirror of the same lines) recomputes P from Q, K and the saved LSE:
+//   dV = Pd^T dO,  dPd = dO V^T,  dS = P o (mask o dPd / keep - delta),  delta = rowsum(dO o O)
+//   dQ = scale * dS K,  dK = scale * dS^T Q
+// with all five contractions on tcgen05 from the same four TMA tiles (Q, K, V, dO); the
+// transposed operands (P^T, dS^T, V as [keys x d], ...) are expressed through MN-major UMMA
+// descriptors, nothing is transposed in memory.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ub {
+
+constexpr int ATT_D = 64;          // head dim (both UNITER configs)
+constexpr int ATT_BM = 128;        // query rows per CTA == TMEM lanes
+constexpr int ATT_BN = 128;        // keys per KV block
+constexpr int ATT_TILE = ATT_BM * ATT_D * 2;   // 16 KB: one 128x64 16-bit tile
+constexpr int ATT_MAXSEQ = 512;    // dropout index pitch == max_position_embeddings
+
+struct AttnParams {
+  const int* cu_seqlens;   // [B+1]
+  int H, nheads, T;
+  void* ctx;               // [T, H] 16-bit
+  float* lse;              // [nheads, T]
+  float scale;             // 1/sqrt(d)
+  uint32_t drop_thr16;
+  float drop_inv_keep;
+  uint32_t seed_lo, seed_hi, stream_lo, stream_hi;
+  // backward only
+  const void* dctx;        // [T, H]
+  void* dqkv;              // [T, 3H]
+};
+
+// element index used to key the attention-probability dropout mask
+__device__ __forceinline__ uint64_t attn_drop_group(int bh, int q, int key8) {
+  return ((static_cast<uint64_t>(bh) * ATT_MAXSEQ + q) * ATT_MAXSEQ + key8) >> 3;
+}
+
+// write 8 consecutive 16-bit values (one 16-byte chunk) of row `r`, columns [col8, col8+8)
+// into a K-major SWIZZLE_128B operand made of 64-column slabs of 128 rows x 128 B.
+__device__ __forceinline__ void st_swz128(uint8_t* base, int r, int col8, uint4 v) {
+  const int slab = col8 >> 6;
+  const int chunk = (col8 & 63) >> 3;
+  uint8_t* p = base + slab * ATT_TILE + r * 128 + ((chunk ^ (r & 7)) << 4);
+  *reinterpret_cast<uint4*>(p) = v;
+}
+
+template <bool kBF16>
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+  const int b = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
+  const int seq0 = p.cu_seqlens[b];
+  const int S = p.cu_seqlens[b + 1] - seq0;
+  if (qt * ATT_BM >= S) return;  // whole CTA exits together, before any barrier / TMEM use
+  const int nkv = (S + ATT_BN - 1) / ATT_BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + ATT_TILE;
+  uint8_t* sV = smem + 2 * ATT_TILE;
+  uint8_t* sP = smem + 3 * ATT_TILE;  // 2 slabs
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + 5 * ATT_TILE);
+  uint64_t* bar_mma = bar_load + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem;          // 128 fp32 columns
+  const uint32_t tO = tmem + 128;    // 64 fp32 columns
+  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+
+  const int qrow = qt * ATT_BM + tid;          // query index inside the sequence
+  const bool q_ok = qrow < S;
+  const int bh = b * p.nheads + head;
+  const float c = p.scale * 1.4426950408889634f;  // scale * log2(e)
+  uint32_t ph_load = 0, ph_mma = 0;
+
+  // ---------------------------------------------------------------- sweep 1: row max / sum
+  float m = -INFINITY, l = 0.f;
+  for (int j = 0; j < nkv; ++j) {
+    const int kv_len = min(ATT_BN, S - j * ATT_BN);
+    const int n_pad = (kv_len + 15) & ~15;
+    if (tid == 0) {
+      const bool with_v = (nkv == 1);
+      mbar_expect_tx(bar_load, (j == 0 ? ATT_TILE : 0) + ATT_TILE + (with_v ? ATT_TILE : 0));
+      if (j == 0) tma_load_2d(sQ, &tmQKV, bar_load, head * ATT_D, seq0 + qt * ATT_BM);
+      tma_load_2d(sK, &tmQKV, bar_load, p.H + head * ATT_D, seq0 + j * ATT_BN);
+      if (with_v) tma_load_2d(sV, &tmQKV, bar_load, 2 * p.H + head * ATT_D, seq0 + j * ATT_BN);
+      mbar_wait(bar_load, ph_load);
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc(kBF16 ? 1 : 0, 0, 0, ATT_BM, n_pad);
+#pragma unroll
+      for (int k = 0; k < ATT_D / 16; ++k)
+        umma_ss(tS, umma_smem_desc(smem_u32(sQ) + k * 32, 16, 1024),
+                umma_smem_desc(smem_u32(sK) + k * 32, 16, 1024), idesc, k != 0);
+      umma_commit(bar_mma);
+    }
+    ph_load ^= 1;
+    mbar_wait(bar_mma, ph_mma);
+    ph_mma ^= 1;
+    tc_fence_after();
+    // pass A: block max
+    float bm = -INFINITY;
+    for (int cc = 0; cc * 32 < kv_len; ++cc) {
+      uint32_t r[32];
+      tmem_ld32(tS + lane_off + cc * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (cc * 32 + i < kv_len) bm = fmaxf(bm, __uint_as_float(r[i]));
+    }
+    const float m_new = fmaxf(m, bm);
+    float bl = 0.f;
+    for (int cc = 0; cc * 32 < kv_len; ++cc) {
+      uint32_t r[32];
+      tmem_ld32(tS + lane_off + cc * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (cc * 32 + i < kv_len) bl += exp2f((__uint_as_float(r[i]) - m_new) * c);
+    }
+    l = l * exp2f((m - m_new) * c) + bl;
+    m = m_new;
+    if (nkv > 1) {  // S (TMEM) and sK are about to be overwritten
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+    }
+  }
+  const float inv_l = 1.f / l;
+  if (q_ok) p.lse[static_cast<size_t>(head) * p.T + seq0 + qrow] = m * p.scale + logf(l);
+
+  // ---------------------------------------------------------------- sweep 2: P and O = P V
+  for (int j = 0; j < nkv; ++j) {
+    const int kv_len = min(ATT_BN, S - j * ATT_BN);
+    const int n_pad = (kv_len + 15) & ~15;
+    if (nkv > 1) {
+      if (tid == 0) {
+        mbar_expect_tx(bar_load, 2 * ATT_TILE);
+        tma_load_2d(sK, &tmQKV, bar_load, p.H + head * ATT_D, seq0 + j * ATT_BN);
+        tma_load_2d(sV, &tmQKV, bar_load, 2 * p.H + head * ATT_D, seq0 + j * ATT_BN);
+        mbar_wait(bar_load, ph_load);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc(kBF16 ? 1 : 0, 0, 0, ATT_BM, n_pad);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_ss(tS, umma_smem_desc(smem_u32(sQ) + k * 32, 16, 1024),
+                  umma_smem_desc(smem_u32(sK) + k * 32, 16, 1024), idesc, k != 0);
+        umma_commit(bar_mma);
+      }
+      ph_load ^= 1;
+      mbar_wait(bar_mma, ph_mma);
+      ph_mma ^= 1;
+      tc_fence_after();
+    }
+    // probabilities -> 16-bit -> swizzled smem (A operand of P.V)
+    for (int cc = 0; cc * 32 < n_pad; ++cc) {
+      uint32_t r[32];
+      tmem_ld32(tS + lane_off + cc * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int key0 = cc * 32 + g * 8;  // within this KV block
+        if (key0 >= n_pad) break;
+        float pv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float s = __uint_as_float(r[g * 8 + i]);
+          pv[i] = (key0 + i < kv_len) ? exp2f((s - m) * c) * inv_l : 0.f;
+        }
+        if (p.drop_thr16) {
+          DropoutRng rng;
+          rng.k0 = p.seed_lo; rng.k1 = p.seed_hi; rng.s0 = p.stream_lo; rng.s1 = p.stream_hi;
+          const uint4 rnd = rng.draw8(attn_drop_group(bh, qrow, j * ATT_BN + key0));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // round P to 16 bit first (reference: softmax output is fp16, then dropout)
+            const float pr = Elem<kBF16>::to_f(Elem<kBF16>::from_f(pv[i]));
+            pv[i] = (rand16_of(rnd, i) < p.drop_thr16) ? 0.f : pr * p.drop_inv_keep;
+          }
+        }
+        uint4 u;
+        u.x = Elem<kBF16>::pack(pv[0], pv[1]);
+        u.y = Elem<kBF16>::pack(pv[2], pv[3]);
+        u.z = Elem<kBF16>::pack(pv[4], pv[5]);
+        u.w = Elem<kBF16>::pack(pv[6], pv[7]);
+        st_swz128(sP, tid, key0, u);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc(kBF16 ? 1 : 0, 0, 1, ATT_BM, ATT_D);
+      const int nk16 = n_pad >> 4;
+      for (int kk = 0; kk < nk16; ++kk) {
+        const uint32_t a = smem_u32(sP) + (kk >> 2) * ATT_TILE + (kk & 3) * 32;
+        const uint32_t bb = smem_u32(sV) + kk * 2048;
+        umma_ss(tO, umma_smem_desc(a, 16, 1024), umma_smem_desc(bb, 8192, 1024), idesc,
+                (j | kk) != 0);
+      }
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, ph_mma);
+    ph_mma ^= 1;
+    tc_fence_after();
+  }
+
+  // ---------------------------------------------------------------- epilogue: O -> ctx[T, H]
+  {
+    typename Elem<kBF16>::T* out = reinterpret_cast<typename Elem<kBF16>::T*>(p.ctx) +
+                                   static_cast<size_t>(seq0 + qrow) * p.H + head * ATT_D;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      uint32_t r[32];
+      tmem_ld32(tO + lane_off + cc * 32, r);
+      tmem_ld_wait();
+      if (q_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1]));
+          u.y = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3]));
+          u.z = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]));
+          u.w = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(out + cc * 32 + g * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+constexpr int ATT_FWD_SMEM = 5 * ATT_TILE + 64 + 1024;
+
+// =====================================================================================
+// Backward.  One CTA per (128-key block j, head, sequence); loops over 128-query blocks i.
+//   TMEM (512 cols): S[128] | dP[128] | dV[64] | dK[64] | dQ[64]
+//   smem: Q_i, dO_i, K_j, V_j (TMA, 128B swizzle) + Pd and dS written by the softmax threads
+//   (row = query, 64-key slabs) and consumed both K-major (dQ = dS K) and MN-major
+//   (dV = Pd^T dO, dK = dS^T Q) by tcgen05.
+// dQ of a sequence longer than one key block is accumulated with fp32 atomics in `dq_accum`.
+// =====================================================================================
+template <bool kBF16>
+__global__ void __launch_bounds__(128)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const AttnParams p, float* dq_accum) {
+  using T16 = typename Elem<kBF16>::T;
+  const int b = blockIdx.z, head = blockIdx.y, j = blockIdx.x;
+  const int seq0 = p.cu_seqlens[b];
+  const int S = p.cu_seqlens[b + 1] - seq0;
+  if (j * ATT_BN >= S) return;
+  const int nq = (S + ATT_BM - 1) / ATT_BM;
+  const int nkv = (S + ATT_BN - 1) / ATT_BN;
+  const int kv_len = min(ATT_BN, S - j * ATT_BN);
+  const int n_pad = (kv_len + 15) & ~15;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sdO = smem + ATT_TILE;
+  uint8_t* sK = smem + 2 * ATT_TILE;
+  uint8_t* sV = smem + 3 * ATT_TILE;
+  uint8_t* sP = smem + 4 * ATT_TILE;   // 2 slabs
+  uint8_t* sDS = smem + 6 * ATT_TILE;  // 2 slabs
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + 8 * ATT_TILE);
+  uint64_t* bar_mma = bar_load + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
+  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+  const int bh = b * p.nheads + head;
+  const float c = p.scale * 1.4426950408889634f;
+  const uint32_t fmt = kBF16 ? 1 : 0;
+  uint32_t ph_load = 0, ph_mma = 0;
+
+  for (int i = 0; i < nq; ++i) {
+    const int q_len = min(ATT_BM, S - i * ATT_BM);
+    const int q_pad = (q_len + 15) & ~15;
+    const int qrow = i * ATT_BM + tid;
+    const bool q_ok = qrow < S;
+    if (tid == 0) {
+      mbar_expect_tx(bar_load, (i == 0 ? 4 : 2) * ATT_TILE);
+      tma_load_2d(sQ, &tmQKV, bar_load, head * ATT_D, seq0 + i * ATT_BM);
+      tma_load_2d(sdO, &tmDO, bar_load, head * ATT_D, seq0 + i * ATT_BM);
+      if (i == 0) {
+        tma_load_2d(sK, &tmQKV, bar_load, p.H + head * ATT_D, seq0 + j * ATT_BN);
+        tma_load_2d(sV, &tmQKV, bar_load, 2 * p.H + head * ATT_D, seq0 + j * ATT_BN);
+      }
+      mbar_wait(bar_load, ph_load);
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc(fmt, 0, 0, ATT_BM, n_pad);
+#pragma unroll
+      for (int k = 0; k < ATT_D / 16; ++k)   // S = Q K^T
+        umma_ss(tS, umma_smem_desc(smem_u32(sQ) + k * 32, 16, 1024),
+                umma_smem_desc(smem_u32(sK) + k * 32, 16, 1024), idesc, k != 0);
+#pragma unroll
+      for (int k = 0; k < ATT_D / 16; ++k)   // dPd = dO V^T
+        umma_ss(tP, umma_smem_desc(smem_u32(sdO) + k * 32, 16, 1024),
+                umma_smem_desc(smem_u32(sV) + k * 32, 16, 1024), idesc, k != 0);
+      umma_commit(bar_mma);
+    }
+    ph_load ^= 1;
+
+    // delta = rowsum(dO o O) and the saved log-sum-exp, straight from global (overlaps the MMAs)
+    float delta = 0.f, lse2 = 0.f;
+    if (q_ok) {
+      const size_t off = static_cast<size_t>(seq0 + qrow) * p.H + head * ATT_D;
+      const uint4* g_do = reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(p.dctx) + off);
+      const uint4* g_o = reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(p.ctx) + off);
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const uint4 a = __ldg(g_do + v), o = __ldg(g_o + v);
+        float2 x, y;
+        x = Elem<kBF16>::unpack(a.x); y = Elem<kBF16>::unpack(o.x); delta += x.x * y.x + x.y * y.y;
+        x = Elem<kBF16>::unpack(a.y); y = Elem<kBF16>::unpack(o.y); delta += x.x * y.x + x.y * y.y;
+        x = Elem<kBF16>::unpack(a.z); y = Elem<kBF16>::unpack(o.z); delta += x.x * y.x + x.y * y.y;
+        x = Elem<kBF16>::unpack(a.w); y = Elem<kBF16>::unpack(o.w); delta += x.x * y.x + x.y * y.y;
+      }
+      lse2 = p.lse[static_cast<size_t>(head) * p.T + seq0 + qrow] * 1.4426950408889634f;
+    }
+
+    mbar_wait(bar_mma, ph_mma);
+    ph_mma ^= 1;
+    tc_fence_after();
+
+    for (int cc = 0; cc * 32 < n_pad; ++cc) {
+      uint32_t rs[32], rp[32];
+      tmem_ld32(tS + lane_off + cc * 32, rs);
+      tmem_ld32(tP + lane_off + cc * 32, rp);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int key0 = cc * 32 + g * 8;
+        if (key0 >= n_pad) break;
+        float pd[8], ds[8];
+        uint4 rnd = make_uint4(0, 0, 0, 0);
+        if (p.drop_thr16) {
+          DropoutRng rng;
+          rng.k0 = p.seed_lo; rng.k1 = p.seed_hi; rng.s0 = p.stream_lo; rng.s1 = p.stream_hi;
+          rnd = rng.draw8(attn_drop_group(bh, qrow, j * ATT_BN + key0));
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const bool ok = q_ok && (key0 + e < kv_len);
+          float pr = ok ? exp2f(__uint_as_float(rs[g * 8 + e]) * c - lse2) : 0.f;
+          pr = Elem<kBF16>::to_f(Elem<kBF16>::from_f(pr));   // P as the forward rounded it
+          float dp = __uint_as_float(rp[g * 8 + e]);
+          float pdv = pr;
+          if (p.drop_thr16) {
+            const bool drop = rand16_of(rnd, e) < p.drop_thr16;
+            pdv = drop ? 0.f : pr * p.drop_inv_keep;
+            dp = drop ? 0.f : dp * p.drop_inv_keep;
+          }
+          pd[e] = pdv;
+          ds[e] = ok ? pr * (dp - delta) * p.scale : 0.f;
+        }
+        uint4 u;
+        u.x = Elem<kBF16>::pack(pd[0], pd[1]); u.y = Elem<kBF16>::pack(pd[2], pd[3]);
+        u.z = Elem<kBF16>::pack(pd[4], pd[5]); u.w = Elem<kBF16>::pack(pd[6], pd[7]);
+        st_swz128(sP, tid, key0, u);
+        u.x = Elem<kBF16>::pack(ds[0], ds[1]); u.y = Elem<kBF16>::pack(ds[2], ds[3]);
+        u.z = Elem<kBF16>::pack(ds[4], ds[5]); u.w = Elem<kBF16>::pack(ds[6], ds[7]);
+        st_swz128(sDS, tid, key0, u);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      // dV += Pd^T dO ; dK += dS^T Q : A = [queries x keys] read MN-major (M = keys),
+      // B = [queries x d] read MN-major (N = d); contraction over the q_pad query rows.
+      const uint32_t idesc_t = umma_idesc(fmt, 1, 1, ATT_BM, ATT_D);
+      const int nq16 = q_pad >> 4;
+      for (int kk = 0; kk < nq16; ++kk) {
+        umma_ss(tdV, umma_smem_desc(smem_u32(sP) + kk * 2048, ATT_TILE, 1024),
+                umma_smem_desc(smem_u32(sdO) + kk * 2048, 8192, 1024), idesc_t, (i | kk) != 0);
+      }
+      for (int kk = 0; kk < nq16; ++kk) {
+        umma_ss(tdK, umma_smem_desc(smem_u32(sDS) + kk * 2048, ATT_TILE, 1024),
+                umma_smem_desc(smem_u32(sQ) + kk * 2048, 8192, 1024), idesc_t, (i | kk) != 0);
+      }
+      // dQ = dS K : A K-major over keys, B = K_j [keys x d] MN-major
+      const uint32_t idesc_q = umma_idesc(fmt, 0, 1, ATT_BM, ATT_D);
+      const int nk16 = n_pad >> 4;
+      for (int kk = 0; kk < nk16; ++kk) {
+        umma_ss(tdQ, umma_smem_desc(smem_u32(sDS) + (kk >> 2) * ATT_TILE + (kk & 3) * 32, 16, 1024),
+                umma_smem_desc(smem_u32(sK) + kk * 2048, 8192, 1024), idesc_q, kk != 0);
+      }
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, ph_mma);
+    ph_mma ^= 1;
+    tc_fence_after();
+    // dQ_i out (rows = queries)
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      uint32_t r[32];
+      tmem_ld32(tdQ + lane_off + cc * 32, r);
+      tmem_ld_wait();
+      if (q_ok) {
+        if (nkv == 1) {
+          T16* out = reinterpret_cast<T16*>(p.dqkv) + static_cast<size_t>(seq0 + qrow) * (3 * p.H) +
+                     head * ATT_D + cc * 32;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1]));
+            u.y = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3]));
+            u.z = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]));
+            u.w = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7]));
+            *reinterpret_cast<uint4*>(out + g * 8) = u;
+          }
+        } else {
+          float* acc = dq_accum + static_cast<size_t>(seq0 + qrow) * p.H + head * ATT_D + cc * 32;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) atomicAdd(acc + e, __uint_as_float(r[e]));
+        }
+      }
+    }
+    if (i + 1 < nq) {  // next iteration overwrites S / dP / dQ (TMEM) and sQ / sdO / sP / sDS
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+    }
+  }
+
+  // dK_j, dV_j out (rows = keys)
+  {
+    const int key = j * ATT_BN + tid;
+    const bool k_ok = key < S;
+    T16* outk = reinterpret_cast<T16*>(p.dqkv) + static_cast<size_t>(seq0 + key) * (3 * p.H) +
+                p.H + head * ATT_D;
+    T16* outv = outk + p.H;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t r[32];
+        tmem_ld32((which ? tdV : tdK) + lane_off + cc * 32, r);
+        tmem_ld_wait();
+        if (k_ok) {
+          T16* out = (which ? outv : outk) + cc * 32;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1]));
+            u.y = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3]));
+            u.z = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]));
+            u.w = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7]));
+            *reinterpret_cast<uint4*>(out + g * 8) = u;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// dqkv[:, 0:H] (16-bit) = dq_accum (fp32) for sequences spanning several key blocks (others
+// wrote dQ directly).  One CTA per sequence.
+template <bool kBF16>
+__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, void* dqkv,
+                                       const int* __restrict__ cu_seqlens, int H) {
+  const int seq0 = cu_seqlens[blockIdx.x];
+  const int S = cu_seqlens[blockIdx.x + 1] - seq0;
+  if (S <= ATT_BN) return;
+  const int nvec = S * H / 8;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const int row = (v * 8) / H, col = (v * 8) % H;
+    const float* src = acc + static_cast<size_t>(seq0 + row) * H + col;
+    const float4 a = *reinterpret_cast<const float4*>(src);
+    const float4 b = *reinterpret_cast<const float4*>(src + 4);
+    uint4 u;
+    u.x = Elem<kBF16>::pack(a.x, a.y); u.y = Elem<kBF16>::pack(a.z, a.w);
+    u.z = Elem<kBF16>::pack(b.x, b.y); u.w = Elem<kBF16>::pack(b.z, b.w);
+    *reinterpret_cast<uint4*>(reinterpret_cast<typename Elem<kBF16>::T*>(dqkv) +
+                              static_cast<size_t>(seq0 + row) * 3 * H + col) = u;
+  }
+}
+
+constexpr int ATT_BWD_SMEM = 8 * ATT_TILE + 64 + 1024;
+
+}  // namespace ub
+
+extern "C" int ub200_attn_fwd(const ub200_attn_args* args, ub200_stream_t stream_) {
+  using namespace ub;
+  UB_CHECK_ARG(args != nullptr, "attn_fwd: args is NULL");
+  const ub200_attn_args& a = *args;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  UB_CHECK_ARG(a.qkv && a.ctx && a.lse && a.cu_seqlens, "attn_fwd: null pointer");
+  UB_CHECK_ARG(a.batch > 0 && a.total_tokens > 0, "attn_fwd: empty batch");
+  UB_CHECK_ARG(a.num_heads > 0 && a.hidden == a.num_heads * ATT_D,
+               "attn_fwd: head_dim must be 64 (hidden=%d heads=%d)", a.hidden, a.num_heads);
+  UB_CHECK_ARG(a.max_seqlen > 0 && a.max_seqlen <= ATT_MAXSEQ,
+               "attn_fwd: max_seqlen %d outside (0, %d]", a.max_seqlen, ATT_MAXSEQ);
+  UB_CHECK_ARG(a.dtype == UB200_F16 || a.dtype == UB200_BF16, "attn_fwd: bad dtype");
+  UB_CHECK_ARG(a.dropout_p >= 0.f && a.dropout_p < 1.f, "attn_fwd: dropout_p out of range");
+
+  CUtensorMap tm;
+  int rc = make_tma_2d(&tm, a.qkv, a.dtype, a.total_tokens, 3 * a.hidden, 3 * a.hidden, ATT_BM,
+                       ATT_D);
+  if (rc) return rc;
+  AttnParams p{};
+  p.cu_seqlens = a.cu_seqlens;
+  p.H = a.hidden; p.nheads = a.num_heads; p.T = a.total_tokens;
+  p.ctx = a.ctx; p.lse = a.lse;
+  p.scale = 0.125f;
+  if (a.dropout_p > 0.f) {
+    uint32_t thr = static_cast<uint32_t>(a.dropout_p * 65536.0f + 0.5f);
+    if (thr > 65535u) thr = 65535u;
+    if (thr == 0u) thr = 1u;
+    p.drop_thr16 = thr;
+    p.drop_inv_keep = 65536.0f / static_cast<float>(65536u - thr);
+  } else {
+    p.drop_thr16 = 0; p.drop_inv_keep = 1.f;
+  }
+  p.seed_lo = static_cast<uint32_t>(a.rng_seed); p.seed_hi = static_cast<uint32_t>(a.rng_seed >> 32);
+  p.stream_lo = static_cast<uint32_t>(a.rng_stream);
+  p.stream_hi = static_cast<uint32_t>(a.rng_stream >> 32);
+
+  dim3 grid((a.max_seqlen + ATT_BM - 1) / ATT_BM, a.num_heads, a.batch);
+  static bool configured[2] = {false, false};
+  if (a.dtype == UB200_BF16) {
+    if (!configured[1]) {
+      UB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
+      configured[1] = true;
+    }
+    attn_fwd_kernel<true><<<grid, 128, ATT_FWD_SMEM, stream>>>(tm, p);
+  } else {
+    if (!configured[0]) {
+      UB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
+      configured[0] = true;
+    }
+    attn_fwd_kernel<false><<<grid, 128, ATT_FWD_SMEM, stream>>>(tm, p);
+  }
+  UB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int64_t ub200_attn_bwd_workspace_bytes(int32_t total_tokens, int32_t hidden,
+                                                  int32_t max_seqlen) {
+  // fp32 dQ accumulator, only touched when some sequence is longer than one 128-key block
+  if (max_seqlen <= ub::ATT_BN) return 0;
+  return static_cast<int64_t>(total_tokens) * hidden * 4;
+}
+
+extern "C" int ub200_attn_bwd(const ub200_attn_args* args, ub200_stream_t stream_) {
+  using namespace ub;
+  UB_CHECK_ARG(args != nullptr, "attn_bwd: args is NULL");
+  const ub200_attn_args& a = *args;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  UB_CHECK_ARG(a.qkv && a.ctx && a.lse && a.cu_seqlens && a.dctx && a.dqkv, "attn_bwd: null pointer");
+  UB_CHECK_ARG(a.batch > 0 && a.total_tokens > 0, "attn_bwd: empty batch");
+  UB_CHECK_ARG(a.num_heads > 0 && a.hidden == a.num_heads * ATT_D, "attn_bwd: head_dim must be 64");
+  UB_CHECK_ARG(a.max_seqlen > 0 && a.max_seqlen <= ATT_MAXSEQ, "attn_bwd: max_seqlen %d outside (0, %d]",
+               a.max_seqlen, ATT_MAXSEQ);
+  UB_CHECK_ARG(a.dtype == UB200_F16 || a.dtype == UB200_BF16, "attn_bwd: bad dtype");
+  const bool multi = a.max_seqlen > ATT_BN;
+  UB_CHECK_ARG(!multi || a.workspace, "attn_bwd: max_seqlen > 128 needs the dQ workspace");
+
+  CUtensorMap tmQ, tmD;
+  int rc = make_tma_2d(&tmQ, a.qkv, a.dtype, a.total_tokens, 3 * a.hidden, 3 * a.hidden, ATT_BM, ATT_D);
+  if (rc) return rc;
+  rc = make_tma_2d(&tmD, a.dctx, a.dtype, a.total_tokens, a.hidden, a.hidden, ATT_BM, ATT_D);
+  if (rc) return rc;
+  AttnParams p{};
+  p.cu_seqlens = a.cu_seqlens;
+  p.H = a.hidden; p.nheads = a.num_heads; p.T = a.total_tokens;
+  p.ctx = a.ctx; p.lse = a.lse; p.dctx = a.dctx; p.dqkv = a.dqkv;
+  p.scale = 0.125f;
+  if (a.dropout_p > 0.f) {
+    uint32_t thr = static_cast<uint32_t>(a.dropout_p * 65536.0f + 0.5f);
+    if (thr > 65535u) thr = 65535u;
+    if (thr == 0u) thr = 1u;
+    p.drop_thr16 = thr;
+    p.drop_inv_keep = 65536.0f / static_cast<float>(65536u - thr);
+  } else {
+    p.drop_thr16 = 0; p.drop_inv_keep = 1.f;
+  }
+  p.seed_lo = static_cast<uint32_t>(a.rng_seed); p.seed_hi = static_cast<uint32_t>(a.rng_seed >> 32);
+  p.stream_lo = static_cast<uint32_t>(a.rng_stream);
+  p.stream_hi = static_cast<uint32_t>(a.rng_stream >> 32);
+  float* acc = reinterpret_cast<float*>(a.workspace);
+  if (multi)
+    UB_CHECK_CUDA(cudaMemsetAsync(acc, 0, static_cast<size_t>(a.total_tokens) * a.hidden * 4, stream));
+
+  dim3 grid((a.max_seqlen + ATT_BN - 1) / ATT_BN, a.num_heads, a.batch);
+  static bool configured[2] = {false, false};
+  const int di = a.dtype == UB200_BF16 ? 1 : 0;
+  if (!configured[di]) {
+    if (di) UB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
+    else UB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
+    configured[di] = true;
+  }
+  if (di) attn_bwd_kernel<true><<<grid, 128, ATT_BWD_SMEM, stream>>>(tmQ, tmD, p, acc);
+  else attn_bwd_kernel<false><<<grid, 128, ATT_BWD_SMEM, stream>>>(tmQ, tmD, p, acc);
+  UB_CHECK_CUDA(cudaGetLastError());
+  if (multi) {
+    if (di) attn_dq_convert_kernel<true><<<a.batch, 256, 0, stream>>>(acc, a.dqkv, a.cu_seqlens, a.hidden);
+    else attn_dq_convert_kernel<false><<<a.batch, 256, 0, stream>>>(acc, a.dqkv, a.cu_seqlens, a.hidden);
+    UB_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}

@@ -1,0 +1,444 @@
+// HBM-bound row-wise kernels of the encoder path (16-byte vector loads, fp32 statistics):
+//   ln_fwd        y = LayerNorm(x) * gamma + beta              (apex FusedLayerNorm semantics:
+//                 biased variance, eps inside the sqrt — model/layer.py:108,114,149,155)
+//   ln_bwd        dx (and dropout-masked dx), dgamma, dbeta, column-sum of the masked dx
+//                 (= bias gradient of the Linear that fed the residual sum), one pass
+//   gather_rows   dst[r] = idx[r] >= 0 ? src[idx[r]] : 0     (pack / unpack between the padded
+//                 [B, L, H] view of the reference API and the packed [T, H] layout; bit-exact)
+//   colsum        out[n] += sum_m x[m, n]                       (bias gradient of the QKV projection)
+//   cvt           16-bit <- fp32 (+ optional accumulate): small-gradient finalisation
+// One warp per row; a lane owns the same columns in every row it visits so that the column
+// reductions of ln_bwd stay in registers until one smem + atomic step per CTA.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ub {
+
+constexpr int LN_MAX_VEC = 4;  // per lane: 4 x 8 columns -> H <= 1024
+constexpr float LN_EPS = 1e-12f;
+
+template <bool kBF16>
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  float2 t;
+  t = Elem<kBF16>::unpack(u.x); f[0] = t.x; f[1] = t.y;
+  t = Elem<kBF16>::unpack(u.y); f[2] = t.x; f[3] = t.y;
+  t = Elem<kBF16>::unpack(u.z); f[4] = t.x; f[5] = t.y;
+  t = Elem<kBF16>::unpack(u.w); f[6] = t.x; f[7] = t.y;
+}
+template <bool kBF16>
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = Elem<kBF16>::pack(f[0], f[1]); u.y = Elem<kBF16>::pack(f[2], f[3]);
+  u.z = Elem<kBF16>::pack(f[4], f[5]); u.w = Elem<kBF16>::pack(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------ LayerNorm fwd
+template <bool kBF16>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const void* __restrict__ x_, const void* __restrict__ gamma_,
+              const void* __restrict__ beta_, void* __restrict__ y_, int rows, int H) {
+  using T16 = typename Elem<kBF16>::T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const int nvec = H >> 3;
+  const uint4* x = reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(x_) +
+                                                  static_cast<size_t>(row) * H);
+  float v[LN_MAX_VEC][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      unpack8<kBF16>(__ldg(x + vi), v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += v[i][e];
+    }
+  }
+  const float mean = warp_sum(sum) / H;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i)
+    if (lane + i * 32 < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; sq += d * d; }
+    }
+  const float rstd = rsqrtf(warp_sum(sq) / H + LN_EPS);
+  const uint4* g = reinterpret_cast<const uint4*>(gamma_);
+  const uint4* bt = reinterpret_cast<const uint4*>(beta_);
+  uint4* y = reinterpret_cast<uint4*>(reinterpret_cast<T16*>(y_) + static_cast<size_t>(row) * H);
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      float gg[8], bb[8], o[8];
+      unpack8<kBF16>(__ldg(g + vi), gg);
+      unpack8<kBF16>(__ldg(bt + vi), bb);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * gg[e] + bb[e];
+      y[vi] = pack8<kBF16>(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ LayerNorm bwd
+struct LnBwdParams {
+  const void* dy;      // [rows, H]
+  const void* x;       // [rows, H]  pre-LN sum saved by the forward
+  const void* gamma;   // [H]
+  void* dx;            // [rows, H]  gradient wrt the pre-LN sum (residual branch)
+  void* dx_drop;       // [rows, H]  dx o dropout-mask / keep (Linear branch); NULL if p == 0
+  float* dgamma;       // [H] fp32, atomically accumulated
+  float* dbeta;        // [H]
+  float* dbias;        // [H] column sum of the Linear-branch gradient; may be NULL
+  int rows, H;
+  uint32_t drop_thr16;
+  float drop_inv_keep;
+  uint32_t seed_lo, seed_hi, stream_lo, stream_hi;
+};
+
+template <bool kBF16>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const LnBwdParams p) {
+  using T16 = typename Elem<kBF16>::T;
+  __shared__ float red[3][8][32 * 8 + 1];  // [quantity][warp][lane*8+e] for one vector slot
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  const int H = p.H, nvec = H >> 3;
+  float gam[LN_MAX_VEC][8];
+  float acc_g[LN_MAX_VEC][8], acc_b[LN_MAX_VEC][8], acc_d[LN_MAX_VEC][8];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(p.gamma) + vi), gam[i]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { acc_g[i][e] = 0.f; acc_b[i][e] = 0.f; acc_d[i][e] = 0.f; }
+  }
+  DropoutRng rng;
+  rng.k0 = p.seed_lo; rng.k1 = p.seed_hi; rng.s0 = p.stream_lo; rng.s1 = p.stream_hi;
+  rng.thr16 = p.drop_thr16; rng.inv_keep = p.drop_inv_keep;
+
+  for (int row = blockIdx.x * nwarps + warp; row < p.rows; row += gridDim.x * nwarps) {
+    const uint4* xr = reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(p.x) +
+                                                     static_cast<size_t>(row) * H);
+    const uint4* dyr = reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(p.dy) +
+                                                      static_cast<size_t>(row) * H);
+    float xv[LN_MAX_VEC][8], dv[LN_MAX_VEC][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        unpack8<kBF16>(__ldg(xr + vi), xv[i]);
+        unpack8<kBF16>(__ldg(dyr + vi), dv[i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += xv[i][e];
+      }
+    }
+    const float mean = warp_sum(sum) / H;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i)
+      if (lane + i * 32 < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float d = xv[i][e] - mean; sq += d * d; }
+      }
+    const float rstd = rsqrtf(warp_sum(sq) / H + LN_EPS);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i)
+      if (lane + i * 32 < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = (xv[i][e] - mean) * rstd;
+          const float g = dv[i][e] * gam[i][e];
+          s1 += g; s2 += g * xh;
+          acc_g[i][e] += dv[i][e] * xh;
+          acc_b[i][e] += dv[i][e];
+          xv[i][e] = xh;           // keep x-hat
+          dv[i][e] = g;            // keep dy * gamma
+        }
+      }
+    s1 = warp_sum(s1) / H;
+    s2 = warp_sum(s2) / H;
+    uint4* dxr = reinterpret_cast<uint4*>(reinterpret_cast<T16*>(p.dx) + static_cast<size_t>(row) * H);
+    uint4* ddr = p.dx_drop ? reinterpret_cast<uint4*>(reinterpret_cast<T16*>(p.dx_drop) +
+                                                      static_cast<size_t>(row) * H)
+                           : nullptr;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = rstd * (dv[i][e] - s1 - xv[i][e] * s2);
+        dxr[vi] = pack8<kBF16>(o);
+        if (ddr) {
+          const uint64_t el = static_cast<uint64_t>(row) * H + vi * 8;
+          const uint4 rnd = rng.draw8(el >> 3);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            o[e] = (rand16_of(rnd, e) < rng.thr16) ? 0.f : o[e] * rng.inv_keep;
+          ddr[vi] = pack8<kBF16>(o);
+        }
+        if (p.dbias) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)  // what the Linear branch sees after 16-bit rounding
+            acc_d[i][e] += Elem<kBF16>::to_f(Elem<kBF16>::from_f(o[e]));
+        }
+      }
+    }
+  }
+
+  // CTA reduction over warps, one vector slot at a time, then one atomic per column per CTA
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC; ++i) {
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      red[0][warp][lane * 8 + e] = acc_g[i][e];
+      red[1][warp][lane * 8 + e] = acc_b[i][e];
+      red[2][warp][lane * 8 + e] = acc_d[i][e];
+    }
+    __syncthreads();
+    // 256 threads <-> 256 columns of this slot
+    const int colslot = threadIdx.x;            // lane*8 + e
+    const int col = (colslot >> 3) * 8 + (colslot & 7) + i * 256;
+    if (col < H) {
+      float a = 0.f, b = 0.f, d = 0.f;
+      for (int w = 0; w < nwarps; ++w) {
+        a += red[0][w][colslot]; b += red[1][w][colslot]; d += red[2][w][colslot];
+      }
+      atomicAdd(p.dgamma + col, a);
+      atomicAdd(p.dbeta + col, b);
+      if (p.dbias) atomicAdd(p.dbias + col, d);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ gather rows
+template <int kDummy>
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                   const int* __restrict__ idx, int rows, int vec_per_row) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const int s = idx[row];
+  uint4* d = dst + static_cast<size_t>(row) * vec_per_row;
+  if (s >= 0) {
+    const uint4* sp = src + static_cast<size_t>(s) * vec_per_row;
+    for (int v = lane; v < vec_per_row; v += 32) d[v] = __ldg(sp + v);
+  } else {
+    for (int v = lane; v < vec_per_row; v += 32) d[v] = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------ column sum
+template <bool kBF16>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const void* __restrict__ x_, float* __restrict__ out, int rows, int N, int ld,
+              int rows_per_cta) {
+  using T16 = typename Elem<kBF16>::T;
+  // CTA = 32 column-vectors (256 columns) x 8 row lanes
+  __shared__ float red[8][256 + 1];
+  const int cv = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col0 = (blockIdx.x * 32 + cv) * 8;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(rows, r0 + rows_per_cta);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col0 < N) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      float f[8];
+      unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(x_) +
+                                                          static_cast<size_t>(r) * ld + col0)), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[rl][cv * 8 + e] = acc[e];
+  __syncthreads();
+  const int c = threadIdx.x;
+  const int col = blockIdx.x * 256 + c;
+  if (col < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    atomicAdd(out + col, s);
+  }
+}
+
+// ------------------------------------------------------------------------------ fp32 -> 16-bit
+template <bool kBF16>
+__global__ void __launch_bounds__(256)
+cvt_kernel(const float* __restrict__ src, void* __restrict__ dst_, long long n, int accumulate) {
+  using T16 = typename Elem<kBF16>::T;
+  T16* dst = reinterpret_cast<T16*>(dst_);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v = src[i];
+    if (accumulate) v += Elem<kBF16>::to_f(dst[i]);
+    dst[i] = Elem<kBF16>::from_f(v);
+  }
+}
+
+// ------------------------------------------------------------------------------ dst = a + b
+template <bool kBF16>
+__global__ void __launch_bounds__(256)
+add16_kernel(uint4* __restrict__ dst, const uint4* __restrict__ a, const uint4* __restrict__ b,
+             long long nvec) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float x[8], y[8];
+    unpack8<kBF16>(a[i], x);
+    unpack8<kBF16>(__ldg(b + i), y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] += y[e];
+    dst[i] = pack8<kBF16>(x);
+  }
+}
+
+// ------------------------------------------------------------------------------ launchers
+int launch_ln_fwd(int dtype, const void* x, const void* gamma, const void* beta, void* y, int rows,
+                  int H, cudaStream_t stream) {
+  if (H % 8 != 0 || H > LN_MAX_VEC * 256 || rows <= 0)
+    return set_error(UB200_EUNSUPPORTED, "ln_fwd: need rows > 0, H %% 8 == 0 and H <= %d (H=%d)",
+                     LN_MAX_VEC * 256, H);
+  const int grid = (rows + 7) / 8;
+  if (dtype == UB200_BF16) ln_fwd_kernel<true><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, H);
+  else ln_fwd_kernel<false><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, H);
+  UB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_ln_bwd(int dtype, const LnBwdParams& p, cudaStream_t stream) {
+  if (p.H % 8 != 0 || p.H > LN_MAX_VEC * 256 || p.rows <= 0)
+    return set_error(UB200_EUNSUPPORTED, "ln_bwd: need rows > 0, H %% 8 == 0 and H <= %d (H=%d)",
+                     LN_MAX_VEC * 256, p.H);
+  int grid = (p.rows + 7) / 8;
+  const int cap = num_sms() * 2;
+  if (grid > cap) grid = cap;
+  if (dtype == UB200_BF16) ln_bwd_kernel<true><<<grid, 256, 0, stream>>>(p);
+  else ln_bwd_kernel<false><<<grid, 256, 0, stream>>>(p);
+  UB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_gather_rows(const void* src, void* dst, const int* idx, int rows, int row_bytes,
+                       cudaStream_t stream) {
+  if (row_bytes % 16 != 0 || rows <= 0)
+    return set_error(UB200_EINVAL, "gather_rows: rows > 0 and row_bytes %% 16 == 0 required");
+  gather_rows_kernel<0><<<(rows + 7) / 8, 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), idx, rows, row_bytes / 16);
+  UB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_colsum(int dtype, const void* x, float* out, int rows, int N, int ld, cudaStream_t stream) {
+  if (N % 8 != 0 || ld % 8 != 0 || rows <= 0)
+    return set_error(UB200_EINVAL, "colsum: rows > 0, N %% 8 == 0, ld %% 8 == 0 required");
+  const int gx = (N + 255) / 256;
+  int gy = (2 * num_sms() + gx - 1) / gx;
+  if (gy > (rows + 31) / 32) gy = (rows + 31) / 32;
+  if (gy < 1) gy = 1;
+  const int rpc = (rows + gy - 1) / gy;
+  dim3 grid(gx, gy);
+  if (dtype == UB200_BF16) colsum_kernel<true><<<grid, 256, 0, stream>>>(x, out, rows, N, ld, rpc);
+  else colsum_kernel<false><<<grid, 256, 0, stream>>>(x, out, rows, N, ld, rpc);
+  UB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_cvt(int dtype, const float* src, void* dst, long long n, int accumulate,
+               cudaStream_t stream) {
+  if (n <= 0) return 0;
+  long long blocks = (n + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (dtype == UB200_BF16)
+    cvt_kernel<true><<<static_cast<int>(blocks), 256, 0, stream>>>(src, dst, n, accumulate);
+  else
+    cvt_kernel<false><<<static_cast<int>(blocks), 256, 0, stream>>>(src, dst, n, accumulate);
+  UB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_add16(int dtype, void* dst, const void* a, const void* b, long long n, cudaStream_t stream) {
+  if (n % 8 != 0) return set_error(UB200_EINVAL, "add16: n %% 8 != 0");
+  const long long nvec = n / 8;
+  long long blocks = (nvec + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (dtype == UB200_BF16)
+    add16_kernel<true><<<static_cast<int>(blocks), 256, 0, stream>>>(
+        reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(a),
+        reinterpret_cast<const uint4*>(b), nvec);
+  else
+    add16_kernel<false><<<static_cast<int>(blocks), 256, 0, stream>>>(
+        reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(a),
+        reinterpret_cast<const uint4*>(b), nvec);
+  UB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ub
+
+// ------------------------------------------------------------------------------ C ABI
+extern "C" int ub200_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y,
+                                   int32_t rows, int32_t hidden, int32_t dtype,
+                                   ub200_stream_t stream) {
+  UB_CHECK_ARG(x && gamma && beta && y, "layernorm_fwd: null pointer");
+  return ub::launch_ln_fwd(dtype, x, gamma, beta, y, rows, hidden,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ub200_layernorm_bwd(const ub200_ln_bwd_args* a, ub200_stream_t stream) {
+  UB_CHECK_ARG(a && a->dy && a->x && a->gamma && a->dx && a->dgamma && a->dbeta,
+               "layernorm_bwd: null pointer");
+  ub::LnBwdParams p{};
+  p.dy = a->dy; p.x = a->x; p.gamma = a->gamma; p.dx = a->dx;
+  p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.dbias = a->dbias;
+  p.rows = a->rows; p.H = a->hidden;
+  if (a->dropout_p > 0.f) {
+    UB_CHECK_ARG(a->dx_drop, "layernorm_bwd: dropout_p > 0 needs dx_drop");
+    uint32_t thr = static_cast<uint32_t>(a->dropout_p * 65536.0f + 0.5f);
+    if (thr > 65535u) thr = 65535u;
+    p.dx_drop = a->dx_drop;
+    p.drop_thr16 = thr;
+    p.drop_inv_keep = 65536.0f / static_cast<float>(65536u - thr);
+  } else {
+    p.dx_drop = nullptr; p.drop_thr16 = 0; p.drop_inv_keep = 1.f;
+  }
+  p.seed_lo = static_cast<uint32_t>(a->rng_seed); p.seed_hi = static_cast<uint32_t>(a->rng_seed >> 32);
+  p.stream_lo = static_cast<uint32_t>(a->rng_stream);
+  p.stream_hi = static_cast<uint32_t>(a->rng_stream >> 32);
+  return ub::launch_ln_bwd(a->dtype, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ub200_gather_rows(const void* src, void* dst, const int32_t* index, int32_t rows,
+                                 int32_t row_bytes, ub200_stream_t stream) {
+  UB_CHECK_ARG(src && dst && index, "gather_rows: null pointer");
+  return ub::launch_gather_rows(src, dst, index, rows, row_bytes,
+                                reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ub200_colsum(const void* x, float* out, int32_t rows, int32_t cols, int64_t ld,
+                            int32_t dtype, ub200_stream_t stream) {
+  UB_CHECK_ARG(x && out, "colsum: null pointer");
+  return ub::launch_colsum(dtype, x, out, rows, cols, static_cast<int>(ld),
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ub200_cvt_from_f32(const float* src, void* dst, int64_t n, int32_t accumulate,
+                                  int32_t dtype, ub200_stream_t stream) {
+  UB_CHECK_ARG(src && dst, "cvt_from_f32: null pointer");
+  return ub::launch_cvt(dtype, src, dst, n, accumulate, reinterpret_cast<cudaStream_t>(stream));
+}

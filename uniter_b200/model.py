@@ -1,0 +1,666 @@
+"""Drop-in `UniterModel` for ChenRocks/UNITER running the encoder on libub200 (sm_100a).
+
+Mirrors the reference's Python contract for the hot path:
+
+* ``UniterConfig`` — model/model.py:24-114 (same constructor, ``from_dict`` / ``from_json_file``)
+* ``UniterPreTrainedModel`` — model/model.py:117-214 (``init_weights``, ``from_pretrained`` incl.
+  the gamma/beta rename and the optional ``bert.`` prefix)
+* ``UniterModel(config, img_dim)`` — model/model.py:295-367: same submodule tree, parameter names
+  and shapes (so ``uniter-base.pt`` / ``uniter-large.pt`` load unchanged and name-based weight-decay
+  grouping, optim/misc.py:14-22, keeps working), same ``forward`` signature and return types.
+
+What differs underneath: the encoder stack runs over PACKED valid tokens ([T, H], no padding
+compute) through hand-written CUDA kernels behind a C ABI; rows where ``attention_mask == 0`` are
+returned as zeros (the reference returns garbage there that no head reads).  There is no
+CPU / eager fallback: parameters must be fp16 or bf16 and live on a B200.
+"""
+import copy
+import ctypes as C
+import json
+import logging
+import math
+
+import torch
+from torch import nn
+
+from . import _lib
+
+logger = logging.getLogger(__name__)
+
+
+# ============================================================================ config
+class UniterConfig(object):
+    """Same fields and construction rules as the reference (model/model.py:24-114)."""
+
+    def __init__(self, vocab_size_or_config_json_file, hidden_size=768, num_hidden_layers=12,
+                 num_attention_heads=12, intermediate_size=3072, hidden_act="gelu",
+                 hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1,
+                 max_position_embeddings=512, type_vocab_size=2, initializer_range=0.02):
+        if isinstance(vocab_size_or_config_json_file, str):
+            with open(vocab_size_or_config_json_file, "r", encoding="utf-8") as reader:
+                for key, value in json.loads(reader.read()).items():
+                    self.__dict__[key] = value
+        elif isinstance(vocab_size_or_config_json_file, int):
+            self.vocab_size = vocab_size_or_config_json_file
+            self.hidden_size = hidden_size
+            self.num_hidden_layers = num_hidden_layers
+            self.num_attention_heads = num_attention_heads
+            self.hidden_act = hidden_act
+            self.intermediate_size = intermediate_size
+            self.hidden_dropout_prob = hidden_dropout_prob
+            self.attention_probs_dropout_prob = attention_probs_dropout_prob
+            self.max_position_embeddings = max_position_embeddings
+            self.type_vocab_size = type_vocab_size
+            self.initializer_range = initializer_range
+        else:
+            raise ValueError("First argument must be either a vocabulary size (int) or the path "
+                             "to a pretrained model config file (str)")
+
+    @classmethod
+    def from_dict(cls, json_object):
+        config = UniterConfig(vocab_size_or_config_json_file=-1)
+        for key, value in json_object.items():
+            config.__dict__[key] = value
+        return config
+
+    @classmethod
+    def from_json_file(cls, json_file):
+        with open(json_file, "r", encoding="utf-8") as reader:
+            return cls.from_dict(json.loads(reader.read()))
+
+    def __repr__(self):
+        return str(self.to_json_string())
+
+    def to_dict(self):
+        return copy.deepcopy(self.__dict__)
+
+    def to_json_string(self):
+        return json.dumps(self.to_dict(), indent=2, sort_keys=True) + "\n"
+
+
+_CONFIG_FIELDS = ("vocab_size", "hidden_size", "num_hidden_layers", "num_attention_heads",
+                  "intermediate_size", "hidden_act", "hidden_dropout_prob",
+                  "attention_probs_dropout_prob", "max_position_embeddings", "type_vocab_size",
+                  "initializer_range")
+
+
+class UniterPreTrainedModel(nn.Module):
+    """Weight init + checkpoint loading with the reference's semantics (model/model.py:117-214)."""
+
+    def __init__(self, config, *inputs, **kwargs):
+        super().__init__()
+        missing = [f for f in _CONFIG_FIELDS if not hasattr(config, f)]
+        if missing:  # accepts the reference's own UniterConfig instances (duck-typed)
+            raise ValueError("Parameter config in `{}(config)` should be a UniterConfig; missing "
+                             "fields {}".format(self.__class__.__name__, missing))
+        self.config = config
+
+    def init_weights(self, module):
+        if isinstance(module, (nn.Linear, nn.Embedding)):
+            module.weight.data.normal_(mean=0.0, std=self.config.initializer_range)
+        elif isinstance(module, nn.LayerNorm):
+            module.bias.data.zero_()
+            module.weight.data.fill_(1.0)
+        if isinstance(module, nn.Linear) and module.bias is not None:
+            module.bias.data.zero_()
+
+    @classmethod
+    def from_pretrained(cls, config_file, state_dict, *inputs, **kwargs):
+        config = UniterConfig.from_json_file(config_file)
+        logger.info("Model config {}".format(config))
+        model = cls(config, *inputs, **kwargs)
+        # TF-style names: gamma -> weight, beta -> bias (model/model.py:166-176)
+        state_dict = state_dict.copy()
+        metadata = getattr(state_dict, "_metadata", None)
+        for key in list(state_dict.keys()):
+            new_key = None
+            if "gamma" in key:
+                new_key = key.replace("gamma", "weight")
+            if "beta" in key:
+                new_key = key.replace("beta", "bias")
+            if new_key:
+                state_dict[new_key] = state_dict.pop(key)
+        if metadata is not None:
+            state_dict._metadata = metadata
+        missing_keys, unexpected_keys, error_msgs = [], [], []
+
+        def load(module, prefix=""):
+            local_metadata = {} if metadata is None else metadata.get(prefix[:-1], {})
+            module._load_from_state_dict(state_dict, prefix, local_metadata, True, missing_keys,
+                                         unexpected_keys, error_msgs)
+            for name, child in module._modules.items():
+                if child is not None:
+                    load(child, prefix + name + ".")
+
+        start_prefix = ""
+        if not hasattr(model, "bert") and any(s.startswith("bert.") for s in state_dict.keys()):
+            start_prefix = "bert."
+        load(model, prefix=start_prefix)
+        if missing_keys:
+            logger.info("Weights of {} not initialized from pretrained model: {}".format(
+                model.__class__.__name__, missing_keys))
+        if unexpected_keys:
+            logger.info("Weights from pretrained model not used in {}: {}".format(
+                model.__class__.__name__, unexpected_keys))
+        if error_msgs:
+            raise RuntimeError("Error(s) in loading state_dict for {}:\n\t{}".format(
+                model.__class__.__name__, "\n\t".join(error_msgs)))
+        return model
+
+
+# ============================================================================ parameter containers
+# These modules own the nn.Parameters at the reference's attribute paths.  The encoder-layer
+# containers never run a torch forward: the kernels read the parameters by pointer.
+class BertSelfAttention(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        if config.hidden_size % config.num_attention_heads != 0:
+            raise ValueError("The hidden size (%d) is not a multiple of the number of attention "
+                             "heads (%d)" % (config.hidden_size, config.num_attention_heads))
+        self.num_attention_heads = config.num_attention_heads
+        self.attention_head_size = config.hidden_size // config.num_attention_heads
+        self.all_head_size = config.hidden_size
+        self.query = nn.Linear(config.hidden_size, config.hidden_size)
+        self.key = nn.Linear(config.hidden_size, config.hidden_size)
+        self.value = nn.Linear(config.hidden_size, config.hidden_size)
+        self.dropout = nn.Dropout(config.attention_probs_dropout_prob)
+
+
+class BertSelfOutput(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=1e-12)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+
+
+class BertAttention(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.self = BertSelfAttention(config)
+        self.output = BertSelfOutput(config)
+
+
+class BertIntermediate(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        if config.hidden_act != "gelu":
+            raise ValueError("libub200 implements hidden_act='gelu' (erf form) only, got %r"
+                             % (config.hidden_act,))
+        self.dense = nn.Linear(config.hidden_size, config.intermediate_size)
+
+
+class BertOutput(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.intermediate_size, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=1e-12)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+
+
+class BertLayer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.attention = BertAttention(config)
+        self.intermediate = BertIntermediate(config)
+        self.output = BertOutput(config)
+
+
+class BertPooler(nn.Module):
+    """tanh(dense(x[:, 0])) — model/layer.py:173-185.  [B, H] x [H, H]: negligible, plain torch."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+        self.activation = nn.Tanh()
+
+    def forward(self, hidden_states):
+        return self.activation(self.dense(hidden_states[:, 0]))
+
+
+class UniterTextEmbeddings(nn.Module):
+    """model/model.py:217-245."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(config.vocab_size, config.hidden_size, padding_idx=0)
+        self.position_embeddings = nn.Embedding(config.max_position_embeddings, config.hidden_size)
+        self.token_type_embeddings = nn.Embedding(config.type_vocab_size, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=1e-12)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+
+    def forward(self, input_ids, position_ids, token_type_ids=None):
+        if token_type_ids is None:
+            token_type_ids = torch.zeros_like(input_ids)
+        embeddings = (self.word_embeddings(input_ids) + self.position_embeddings(position_ids)
+                      + self.token_type_embeddings(token_type_ids))
+        return self.dropout(self.LayerNorm(embeddings))
+
+
+class UniterImageEmbeddings(nn.Module):
+    """model/model.py:248-272."""
+
+    def __init__(self, config, img_dim):
+        super().__init__()
+        self.img_linear = nn.Linear(img_dim, config.hidden_size)
+        self.img_layer_norm = nn.LayerNorm(config.hidden_size, eps=1e-12)
+        self.pos_layer_norm = nn.LayerNorm(config.hidden_size, eps=1e-12)
+        self.pos_linear = nn.Linear(7, config.hidden_size)
+        self.mask_embedding = nn.Embedding(2, img_dim, padding_idx=0)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=1e-12)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+
+    def forward(self, img_feat, img_pos_feat, type_embeddings, img_masks=None):
+        if img_masks is not None:
+            self.mask_embedding.weight.data[0, :].fill_(0)
+            img_feat = img_feat + self.mask_embedding(img_masks.long())
+        transformed_im = self.img_layer_norm(self.img_linear(img_feat))
+        transformed_pos = self.pos_layer_norm(self.pos_linear(img_pos_feat))
+        embeddings = self.LayerNorm(transformed_im + transformed_pos + type_embeddings)
+        return self.dropout(embeddings)
+
+
+class UniterEncoder(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        layer = BertLayer(config)
+        self.layer = nn.ModuleList([copy.deepcopy(layer) for _ in range(config.num_hidden_layers)])
+
+
+# ============================================================================ ctypes mirrors
+class _LayerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("wqkv", "bqkv", "wo", "bo", "ln1_g", "ln1_b", "w1", "b1",
+                                          "w2", "b2", "ln2_g", "ln2_b")]
+
+
+class _LayerGrads(C.Structure):
+    _fields_ = [("dwqkv", C.c_void_p), ("dwo", C.c_void_p), ("dw1", C.c_void_p),
+                ("dw2", C.c_void_p), ("small", C.c_void_p)]
+
+
+class _EncoderDesc(C.Structure):
+    _fields_ = [("hidden", C.c_int32), ("intermediate", C.c_int32), ("num_heads", C.c_int32),
+                ("num_layers", C.c_int32), ("dtype", C.c_int32), ("batch", C.c_int32),
+                ("total_tokens", C.c_int32), ("max_seqlen", C.c_int32),
+                ("cu_seqlens", C.c_void_p), ("hidden_dropout_p", C.c_float),
+                ("attn_dropout_p", C.c_float), ("rng_seed", C.c_uint64), ("rng_offset", C.c_uint64)]
+
+
+_lib_ready = False
+
+
+def _bind():
+    global _lib_ready
+    lib = _lib.load()
+    if not _lib_ready:
+        lib.ub200_encoder_act_bytes_per_layer.restype = C.c_int64
+        lib.ub200_encoder_act_bytes_per_layer.argtypes = [C.POINTER(_EncoderDesc)]
+        lib.ub200_encoder_bwd_scratch_bytes.restype = C.c_int64
+        lib.ub200_encoder_bwd_scratch_bytes.argtypes = [C.POINTER(_EncoderDesc)]
+        lib.ub200_encoder_small_grad_count.restype = C.c_int64
+        lib.ub200_encoder_small_grad_count.argtypes = [C.c_int32, C.c_int32]
+        lib.ub200_encoder_fwd.restype = C.c_int
+        lib.ub200_encoder_fwd.argtypes = [C.POINTER(_EncoderDesc), C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        lib.ub200_encoder_bwd.restype = C.c_int
+        lib.ub200_encoder_bwd.argtypes = [C.POINTER(_EncoderDesc), C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        lib.ub200_gather_rows.restype = C.c_int
+        lib.ub200_gather_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                          C.c_void_p]
+        lib.ub200_cvt_from_f32.restype = C.c_int
+        lib.ub200_cvt_from_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                           C.c_void_p]
+        _lib_ready = True
+    return lib
+
+
+_rng_offset = [0]
+
+
+# ============================================================================ autograd glue
+class _GatherRows(torch.autograd.Function):
+    """dst[r] = src[index[r]] (index >= 0) else 0 — bit-exact row mover (ub200_gather_rows).
+
+    Backward: if `inverse` (an index with dst = inverse-gather of grad) is given, the gradient is
+    itself a row gather (pack <-> unpack are mutually inverse); otherwise rows are scatter-ADDED
+    back, so duplicates in an arbitrary gather_index accumulate like torch.gather's backward."""
+
+    @staticmethod
+    def forward(ctx, src, index, n_src_rows, inverse):
+        lib = _bind()
+        src = src.contiguous()
+        rows = index.numel()
+        H = src.size(-1)
+        dst = torch.empty(rows, H, device=src.device, dtype=src.dtype)
+        _lib.check(lib.ub200_gather_rows(src.data_ptr(), dst.data_ptr(), index.data_ptr(), rows,
+                                         H * src.element_size(), _lib.current_stream()))
+        ctx.n_src_rows = n_src_rows
+        ctx.src_shape = src.shape
+        ctx.has_inverse = inverse is not None
+        ctx.save_for_backward(inverse if inverse is not None else index)
+        return dst
+
+    @staticmethod
+    def backward(ctx, grad):
+        (index,) = ctx.saved_tensors
+        grad = grad.contiguous()
+        H = grad.size(-1)
+        if ctx.has_inverse:
+            lib = _bind()
+            out = torch.empty(ctx.n_src_rows, H, device=grad.device, dtype=grad.dtype)
+            _lib.check(lib.ub200_gather_rows(grad.data_ptr(), out.data_ptr(), index.data_ptr(),
+                                             ctx.n_src_rows, H * grad.element_size(),
+                                             _lib.current_stream()))
+        else:
+            out = torch.zeros(ctx.n_src_rows, H, device=grad.device, dtype=grad.dtype)
+            valid = (index >= 0).unsqueeze(1)
+            out.index_add_(0, index.clamp(min=0).long(), grad * valid)
+        return out.view(ctx.src_shape), None, None, None
+
+
+class _EncoderStack(torch.autograd.Function):
+    """NL x BertLayer over packed tokens: one C-ABI call forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, model, meta, want_all, need_grad):
+        lib = _bind()
+        cfg = model.config
+        T, H = x.shape
+        NL = cfg.num_hidden_layers
+        training = model.training
+        p_hidden = float(model.encoder.layer[0].output.dropout.p) if training else 0.0
+        p_attn = float(model.encoder.layer[0].attention.self.dropout.p) if training else 0.0
+        _rng_offset[0] += 1
+        desc = _EncoderDesc(
+            hidden=H, intermediate=cfg.intermediate_size, num_heads=cfg.num_attention_heads,
+            num_layers=NL, dtype=_lib.dtype_code(x.dtype), batch=meta["batch"], total_tokens=T,
+            max_seqlen=meta["max_seqlen"], cu_seqlens=meta["cu_seqlens"].data_ptr(),
+            hidden_dropout_p=p_hidden, attn_dropout_p=p_attn,
+            rng_seed=torch.cuda.initial_seed() & 0xFFFFFFFFFFFFFFFF, rng_offset=_rng_offset[0])
+        weights = model._weight_table()
+        act_bytes = lib.ub200_encoder_act_bytes_per_layer(C.byref(desc))
+        act = torch.empty((NL if need_grad else 1) * act_bytes, device=x.device, dtype=torch.uint8)
+        outs = torch.empty(NL, T, H, device=x.device, dtype=x.dtype)
+        out_ptrs = (C.c_void_p * NL)(*[outs[l].data_ptr() for l in range(NL)])
+        x = x.contiguous()
+        _lib.check(lib.ub200_encoder_fwd(C.byref(desc), weights, x.data_ptr(), out_ptrs,
+                                         act.data_ptr(), 1 if need_grad else 0,
+                                         _lib.current_stream()))
+        ctx.model = model
+        ctx.desc = desc
+        ctx.meta = meta
+        ctx.want_all = want_all
+        ctx.save_for_backward(x, outs, act)
+        ctx.out_ptrs = out_ptrs
+        if want_all:
+            return outs
+        return outs[NL - 1]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _bind()
+        model = ctx.model
+        x, outs, act = ctx.saved_tensors
+        desc = ctx.desc
+        NL = desc.num_layers
+        T, H = x.shape
+        grad_out = grad_out.contiguous()
+        if ctx.want_all:
+            d_ptrs = (C.c_void_p * NL)(*[grad_out[l].data_ptr() for l in range(NL)])
+        else:
+            d_ptrs = (C.c_void_p * NL)(*([None] * (NL - 1) + [grad_out.data_ptr()]))
+        grads, accumulate = model._grad_table()
+        scratch = torch.empty(lib.ub200_encoder_bwd_scratch_bytes(C.byref(desc)), device=x.device,
+                              dtype=torch.uint8)
+        dx = torch.empty_like(x)
+        _lib.check(lib.ub200_encoder_bwd(C.byref(desc), model._weight_table(), grads, x.data_ptr(),
+                                         ctx.out_ptrs, act.data_ptr(), d_ptrs, dx.data_ptr(),
+                                         scratch.data_ptr(), 1 if accumulate else 0,
+                                         _lib.current_stream()))
+        model._finish_grads(accumulate)
+        return dx, None, None, None, None, None
+
+
+# ============================================================================ the model
+class UniterModel(UniterPreTrainedModel):
+    """Joint vision-language encoder — same constructor / forward as model/model.py:295-367."""
+
+    def __init__(self, config, img_dim):
+        super().__init__(config)
+        if config.hidden_size != 64 * config.num_attention_heads:
+            raise ValueError("libub200 attention kernels need head_dim 64 (hidden_size=%d, heads=%d)"
+                             % (config.hidden_size, config.num_attention_heads))
+        self.embeddings = UniterTextEmbeddings(config)
+        self.img_embeddings = UniterImageEmbeddings(config, img_dim)
+        self.encoder = UniterEncoder(config)
+        self.pooler = BertPooler(config)
+        self.apply(self.init_weights)
+        self._packed_key = None
+        self._wtable = None
+        self._arena = None
+
+    # ------------------------------------------------------------------ parameter / gradient arenas
+    _BIG = ("wqkv", "wo", "w1", "w2")
+
+    def _layer_params(self, layer):
+        a, o = layer.attention, layer.output
+        return dict(q_w=a.self.query.weight, k_w=a.self.key.weight, v_w=a.self.value.weight,
+                    q_b=a.self.query.bias, k_b=a.self.key.bias, v_b=a.self.value.bias,
+                    wo=a.output.dense.weight, bo=a.output.dense.bias,
+                    ln1_g=a.output.LayerNorm.weight, ln1_b=a.output.LayerNorm.bias,
+                    w1=layer.intermediate.dense.weight, b1=layer.intermediate.dense.bias,
+                    w2=o.dense.weight, b2=o.dense.bias, ln2_g=o.LayerNorm.weight,
+                    ln2_b=o.LayerNorm.bias)
+
+    def _weight_table(self):
+        """ctypes array of per-layer weight pointers.  query/key/value are re-homed (once, and
+        again after any ``.half()`` / ``.to()`` that re-allocates them) as views of one [3H, H]
+        and one [3H] buffer so the fused QKV projection reads them in place."""
+        layers = self.encoder.layer
+        key = tuple(l.attention.self.query.weight.data_ptr() for l in layers) + \
+            tuple(l.output.dense.weight.data_ptr() for l in layers)
+        if self._wtable is not None and key == self._packed_key:
+            return self._wtable
+        H = self.config.hidden_size
+        table = (_LayerWeights * len(layers))()
+        p0 = layers[0].attention.self.query.weight
+        if not p0.is_cuda or p0.dtype not in (torch.float16, torch.bfloat16):
+            raise RuntimeError("UniterModel (libub200) needs fp16/bf16 parameters on a CUDA device "
+                               "(got %s on %s); call .cuda().half() or .bfloat16() — there is no "
+                               "fp32 / CPU fallback" % (p0.dtype, p0.device))
+        for i, layer in enumerate(layers):
+            P = self._layer_params(layer)
+            qw, kw, vw = P["q_w"], P["k_w"], P["v_w"]
+            nb = qw.numel() * qw.element_size()
+            contiguous = (kw.data_ptr() == qw.data_ptr() + nb and vw.data_ptr() == kw.data_ptr() + nb)
+            if not contiguous:
+                buf = torch.cat([qw.data, kw.data, vw.data], 0)  # [3H, H]
+                qw.data, kw.data, vw.data = buf[:H], buf[H:2 * H], buf[2 * H:]
+            qb, kb, vb = P["q_b"], P["k_b"], P["v_b"]
+            nb = qb.numel() * qb.element_size()
+            if not (kb.data_ptr() == qb.data_ptr() + nb and vb.data_ptr() == kb.data_ptr() + nb):
+                buf = torch.cat([qb.data, kb.data, vb.data], 0)
+                qb.data, kb.data, vb.data = buf[:H], buf[H:2 * H], buf[2 * H:]
+            t = table[i]
+            t.wqkv, t.bqkv = qw.data_ptr(), qb.data_ptr()
+            for name in ("wo", "bo", "ln1_g", "ln1_b", "w1", "b1", "w2", "b2", "ln2_g", "ln2_b"):
+                if not P[name].is_contiguous():
+                    P[name].data = P[name].data.contiguous()
+                setattr(t, name, P[name].data_ptr())
+        self._wtable = table
+        self._packed_key = tuple(l.attention.self.query.weight.data_ptr() for l in layers) + \
+            tuple(l.output.dense.weight.data_ptr() for l in layers)
+        self._arena = None  # gradient arena must match the (possibly new) dtype / device
+        return table
+
+    def _build_arena(self):
+        """Flat 16-bit gradient arena for all encoder-layer parameters (the unit of the NCCL
+        gradient allreduce) + fp32 accumulators for the small (bias / LayerNorm) gradients."""
+        lib = _bind()
+        cfg = self.config
+        H, I, NL = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
+        p0 = self.encoder.layer[0].attention.self.query.weight
+        small_n = lib.ub200_encoder_small_grad_count(H, I)
+        big_n = 3 * H * H + H * H + I * H + H * I
+        per_layer = big_n + small_n
+        flat = torch.zeros(NL * per_layer, device=p0.device, dtype=p0.dtype)
+        small32 = torch.zeros(NL * small_n, device=p0.device, dtype=torch.float32)
+        gtable = (_LayerGrads * NL)()
+        views = []  # (param, grad_view)
+        for i, layer in enumerate(self.encoder.layer):
+            P = self._layer_params(layer)
+            base = i * per_layer
+            o = base
+            dwqkv = flat[o:o + 3 * H * H].view(3 * H, H); o += 3 * H * H
+            dwo = flat[o:o + H * H].view(H, H); o += H * H
+            dw1 = flat[o:o + I * H].view(I, H); o += I * H
+            dw2 = flat[o:o + H * I].view(H, I); o += H * I
+            small16 = flat[o:o + small_n]
+            views += [(P["q_w"], dwqkv[:H]), (P["k_w"], dwqkv[H:2 * H]), (P["v_w"], dwqkv[2 * H:]),
+                      (P["wo"], dwo), (P["w1"], dw1), (P["w2"], dw2)]
+            s = 0
+            for name, n in (("q_b", H), ("k_b", H), ("v_b", H), ("bo", H), ("ln1_g", H), ("ln1_b", H),
+                            ("b1", I), ("b2", H), ("ln2_g", H), ("ln2_b", H)):
+                views.append((P[name], small16[s:s + n]))
+                s += n
+            g = gtable[i]
+            g.dwqkv, g.dwo, g.dw1, g.dw2 = dwqkv.data_ptr(), dwo.data_ptr(), dw1.data_ptr(), dw2.data_ptr()
+            g.small = small32[i * small_n:(i + 1) * small_n].data_ptr()
+        self._arena = dict(flat=flat, small32=small32, gtable=gtable, views=views, small_n=small_n,
+                           per_layer=per_layer, big_n=big_n)
+        return self._arena
+
+    def grad_arena(self):
+        """The flat gradient buffer of the encoder layers (what gets all-reduced)."""
+        if self._arena is None:
+            self._build_arena()
+        return self._arena["flat"]
+
+    def _grad_table(self):
+        if self._arena is None:
+            self._build_arena()
+        A = self._arena
+        # accumulate iff the parameters still carry OUR arena views as .grad (i.e. zero_grad() was
+        # not called with set_to_none since the last backward)
+        p, v = A["views"][0]
+        accumulate = p.grad is not None and p.grad.data_ptr() == v.data_ptr()
+        A["small32"].zero_()
+        return A["gtable"], accumulate
+
+    def _finish_grads(self, accumulate):
+        lib = _bind()
+        A = self._arena
+        NL = self.config.num_hidden_layers
+        flat, small32, n = A["flat"], A["small32"], A["small_n"]
+        dt = _lib.dtype_code(flat.dtype)
+        stream = _lib.current_stream()
+        for i in range(NL):
+            dst = flat[i * A["per_layer"] + A["big_n"]:(i + 1) * A["per_layer"]]
+            _lib.check(lib.ub200_cvt_from_f32(small32[i * n:(i + 1) * n].data_ptr(), dst.data_ptr(), n,
+                                              1 if accumulate else 0, dt, stream))
+        if not accumulate:
+            for p, v in A["views"]:
+                if p.requires_grad:
+                    if p.grad is None:
+                        p.grad = v
+                    else:          # a foreign gradient tensor is already there: add into it
+                        p.grad.add_(v)
+
+    # ------------------------------------------------------------------ embeddings (reference API)
+    def _compute_txt_embeddings(self, input_ids, position_ids, txt_type_ids=None):
+        return self.embeddings(input_ids, position_ids, txt_type_ids)
+
+    def _compute_img_embeddings(self, img_feat, img_pos_feat, img_masks=None, img_type_ids=None):
+        if img_type_ids is None:
+            img_type_ids = torch.ones_like(img_feat[:, :, 0].long())
+        img_type_embeddings = self.embeddings.token_type_embeddings(img_type_ids)
+        return self.img_embeddings(img_feat, img_pos_feat, img_type_embeddings, img_masks)
+
+    def _compute_img_txt_embeddings(self, input_ids, position_ids, img_feat, img_pos_feat,
+                                    gather_index, img_masks=None, txt_type_ids=None,
+                                    img_type_ids=None):
+        """Padded [B, L, H] result with the reference's semantics (model/model.py:321-334); the
+        forward pass below never materialises it (it gathers straight into packed rows)."""
+        txt_emb = self._compute_txt_embeddings(input_ids, position_ids, txt_type_ids)
+        img_emb = self._compute_img_embeddings(img_feat, img_pos_feat, img_masks, img_type_ids)
+        cat = torch.cat([txt_emb, img_emb], dim=1)
+        B, Lc, H = cat.shape
+        flat_idx = (gather_index + torch.arange(B, device=cat.device).unsqueeze(1) * Lc).reshape(-1)
+        out = _GatherRows.apply(cat.reshape(B * Lc, H), flat_idx.to(torch.int32).contiguous(), B * Lc, None)
+        return out.view(B, gather_index.size(1), H)
+
+    # ------------------------------------------------------------------ packing metadata
+    @staticmethod
+    def _pack_meta(attention_mask):
+        """Valid-token bookkeeping from the [B, L] attention mask (prefix masks in every reference
+        collate, but any 0/1 pattern is honoured: valid tokens are packed in order).  One small
+        device->host read (the per-sample lengths) — the reference itself syncs every step
+        (train_vqa.py:201)."""
+        B, L = attention_mask.shape
+        am = attention_mask != 0
+        lens = am.sum(1)
+        lens_h = lens.tolist()           # host sync (B integers)
+        T = int(sum(lens_h))
+        dev = attention_mask.device
+        cu = torch.zeros(B + 1, device=dev, dtype=torch.int32)
+        cu[1:] = torch.cumsum(lens, 0)
+        # [T] -> b*L+j ; size is known from the host-side lengths, so no second sync
+        pack_idx = torch.nonzero_static(am.reshape(-1), size=T).squeeze(1).to(torch.int32)
+        unpack_idx = torch.full((B * L,), -1, device=dev, dtype=torch.int32)
+        unpack_idx[pack_idx.long()] = torch.arange(T, device=dev, dtype=torch.int32)
+        return dict(batch=B, L=L, total=T, max_seqlen=max(lens_h) if lens_h else 0,
+                    cu_seqlens=cu, pack_idx=pack_idx, unpack_idx=unpack_idx)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, input_ids, position_ids, img_feat, img_pos_feat, attention_mask,
+                gather_index=None, img_masks=None, output_all_encoded_layers=True,
+                txt_type_ids=None, img_type_ids=None):
+        self._weight_table()  # validates dtype/device, packs q/k/v
+        dtype = self.encoder.layer[0].attention.self.query.weight.dtype
+        meta = self._pack_meta(attention_mask)
+        if meta["total"] == 0:
+            raise ValueError("attention_mask selects no tokens")
+        B, L = meta["batch"], meta["L"]
+        H = self.config.hidden_size
+        if img_feat is not None:
+            img_feat = img_feat.to(dtype)
+            img_pos_feat = img_pos_feat.to(dtype)
+
+        # ---- embeddings (model/model.py:347-360), gathered straight into PACKED rows
+        if input_ids is None:
+            emb = self._compute_img_embeddings(img_feat, img_pos_feat, img_masks, img_type_ids)
+            src, src_idx, pack_inverse = emb.reshape(-1, H), meta["pack_idx"], meta["unpack_idx"]
+            if emb.size(1) != L:
+                raise ValueError("attention_mask length %d != number of regions %d" % (L, emb.size(1)))
+        elif img_feat is None:
+            emb = self._compute_txt_embeddings(input_ids, position_ids, txt_type_ids)
+            src, src_idx, pack_inverse = emb.reshape(-1, H), meta["pack_idx"], meta["unpack_idx"]
+            if emb.size(1) != L:
+                raise ValueError("attention_mask length %d != text length %d" % (L, emb.size(1)))
+        else:
+            txt_emb = self._compute_txt_embeddings(input_ids, position_ids, txt_type_ids)
+            img_emb = self._compute_img_embeddings(img_feat, img_pos_feat, img_masks, img_type_ids)
+            cat = torch.cat([txt_emb, img_emb], dim=1)
+            Lc = cat.size(1)
+            if gather_index.shape != (B, L):
+                raise ValueError("gather_index must be [B, L] like attention_mask")
+            flat_gi = (gather_index + torch.arange(B, device=cat.device).unsqueeze(1) * Lc).reshape(-1)
+            src, src_idx = cat.reshape(-1, H), flat_gi[meta["pack_idx"].long()].to(torch.int32)
+            pack_inverse = None  # arbitrary gather_index may repeat rows: scatter-add backward
+        x = _GatherRows.apply(src, src_idx.contiguous(), src.size(0), pack_inverse)  # [T, H] packed
+
+        # ---- encoder stack on packed tokens
+        if not hasattr(self, "_anchor") or self._anchor.device != x.device:
+            self._anchor = torch.zeros(1, device=x.device, requires_grad=True)
+        # (grad mode is always off inside Function.forward, so decide here whether the backward
+        #  will need the per-layer activations)
+        out = _EncoderStack.apply(x, self._anchor, self, meta, bool(output_all_encoded_layers),
+                                  torch.is_grad_enabled())
+
+        # ---- back to the reference's padded [B, L, H] view (zeros at masked positions)
+        if output_all_encoded_layers:
+            return [_GatherRows.apply(out[l], meta["unpack_idx"], meta["total"],
+                                      meta["pack_idx"]).view(B, L, H) for l in range(out.size(0))]
+        return _GatherRows.apply(out, meta["unpack_idx"], meta["total"], meta["pack_idx"]).view(B, L, H)

@@ -64,3 +64,74 @@ def gemm(a, b, *, a_major=0, b_major=0, bias=None, residual=None, aux=None, out=
         tile_n=int(tile_n), max_ctas=int(max_ctas))
     _lib.check(lib.ub200_gemm(C.byref(args), _lib.current_stream()))
     return (out, out2) if gelu else out
+
+
+def attn_fwd(qkv, cu_seqlens, max_seqlen, num_heads, dropout_p=0.0, rng_seed=0, rng_stream=0):
+    """ctx [T, H], lse [heads, T] = fused varlen attention over packed qkv [T, 3H]."""
+    lib = _lib.load()
+    T, H3 = qkv.shape
+    H = H3 // 3
+    ctx = torch.empty(T, H, device=qkv.device, dtype=qkv.dtype)
+    lse = torch.empty(num_heads, T, device=qkv.device, dtype=torch.float32)
+    a = _lib.AttnArgs(qkv=qkv.data_ptr(), ctx=ctx.data_ptr(), lse=lse.data_ptr(),
+                      cu_seqlens=cu_seqlens.data_ptr(), batch=cu_seqlens.numel() - 1,
+                      total_tokens=T, max_seqlen=max_seqlen, hidden=H, num_heads=num_heads,
+                      dtype=_lib.dtype_code(qkv.dtype), dropout_p=float(dropout_p),
+                      rng_seed=int(rng_seed), rng_stream=int(rng_stream))
+    _lib.check(lib.ub200_attn_fwd(C.byref(a), _lib.current_stream()))
+    return ctx, lse
+
+
+def attn_bwd(qkv, ctx, lse, dctx, cu_seqlens, max_seqlen, num_heads, dropout_p=0.0, rng_seed=0,
+             rng_stream=0):
+    lib = _lib.load()
+    T, H3 = qkv.shape
+    H = H3 // 3
+    dqkv = torch.empty_like(qkv)
+    ws_bytes = lib.ub200_attn_bwd_workspace_bytes(T, H, max_seqlen)
+    ws = torch.empty(max(ws_bytes, 1), device=qkv.device, dtype=torch.uint8)
+    a = _lib.AttnArgs(qkv=qkv.data_ptr(), ctx=ctx.data_ptr(), lse=lse.data_ptr(),
+                      cu_seqlens=cu_seqlens.data_ptr(), batch=cu_seqlens.numel() - 1,
+                      total_tokens=T, max_seqlen=max_seqlen, hidden=H, num_heads=num_heads,
+                      dtype=_lib.dtype_code(qkv.dtype), dropout_p=float(dropout_p),
+                      rng_seed=int(rng_seed), rng_stream=int(rng_stream),
+                      dctx=dctx.data_ptr(), dqkv=dqkv.data_ptr(),
+                      workspace=ws.data_ptr() if ws_bytes else None)
+    _lib.check(lib.ub200_attn_bwd(C.byref(a), _lib.current_stream()))
+    return dqkv
+
+
+def layernorm_fwd(x, gamma, beta):
+    lib = _lib.load()
+    rows, H = x.shape
+    y = torch.empty_like(x)
+    _lib.check(lib.ub200_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                       rows, H, _lib.dtype_code(x.dtype), _lib.current_stream()))
+    return y
+
+
+def layernorm_bwd(dy, x, gamma, dropout_p=0.0, rng_seed=0, rng_stream=0, want_dbias=True):
+    """Returns dx, dx_drop (or None), dgamma, dbeta, dbias (fp32)."""
+    lib = _lib.load()
+    rows, H = x.shape
+    dx = torch.empty_like(x)
+    dx_drop = torch.empty_like(x) if dropout_p > 0 else None
+    dgamma = torch.zeros(H, device=x.device, dtype=torch.float32)
+    dbeta = torch.zeros_like(dgamma)
+    dbias = torch.zeros_like(dgamma) if want_dbias else None
+    a = _lib.LnBwdArgs(dy=dy.data_ptr(), x=x.data_ptr(), gamma=gamma.data_ptr(), dx=dx.data_ptr(),
+                       dx_drop=_lib.ptr(dx_drop), dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(),
+                       dbias=_lib.ptr(dbias), rows=rows, hidden=H, dtype=_lib.dtype_code(x.dtype),
+                       dropout_p=float(dropout_p), rng_seed=int(rng_seed), rng_stream=int(rng_stream))
+    _lib.check(lib.ub200_layernorm_bwd(C.byref(a), _lib.current_stream()))
+    return dx, dx_drop, dgamma, dbeta, dbias
+
+
+def colsum(x, out=None):
+    lib = _lib.load()
+    rows, N = x.shape
+    if out is None:
+        out = torch.zeros(N, device=x.device, dtype=torch.float32)
+    _lib.check(lib.ub200_colsum(x.data_ptr(), out.data_ptr(), rows, N, x.stride(0),
+                                _lib.dtype_code(x.dtype), _lib.current_stream()))
+    return out
