@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Headline benchmark: UNITER-base encoder fwd+bwd samples/s (BASELINE.json configs[1] = C2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype bf16|fp16]
+
+One "step" = one pass of the hot path over one synthetic batch per GPU: H2D (e2e leg only),
+UniterModel forward (embeddings + 12 BertLayers on packed tokens) + MLM head + loss, backward,
+and for N > 1 the gradient allreduce (NCCL, mean) — weak scaling, 64 samples per GPU.
+Prints ONE JSON line on rank 0 (contract in the task statement; extra keys: roofline,
+cpu_baseline, clocks, e2e, gpu_launches, breakdown).
+
+`--impl reference` times the CPU restatement of the reference path (oracle/, kind "port" — the
+reference is Python and cannot travel to the GPU box) on the host cores, bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "uniter_base_encoder_fwd_bwd_samples_per_sec"
+BASE = dict(vocab=28996, H=768, NL=12, heads=12, I=3072, max_pos=512, img_dim=2048)
+C2 = dict(B=64, tl=(12, 28), nbb=(26, 46), seed=1234, mlm_prob=0.15)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--cpu-sample", type=int, default=8, help="samples in the CPU baseline batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--layers", type=int, default=BASE["NL"], help=argparse.SUPPRESS)
+    return ap.parse_args()
+
+
+def algorithmic_flops(lens, NL, H):
+    """F_fwd+bwd = 3 * NL * (24 H^2 T + 4 H sum S^2), valid tokens only."""
+    T = sum(lens)
+    s2 = sum(s * s for s in lens)
+    return 3.0 * NL * (24.0 * H * H * T + 4.0 * H * s2)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            j = json.load(fh)
+        return dict(tflops=j["bf16_tflops"], tflops_sustained=j.get("bf16_tflops_sustained"),
+                    hbm_gbs=j["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
+    return dict(tflops=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0,
+                source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# =============================================================================== CPU (reference) arm
+def cpu_reference_run(args, steps, warmup, sample_B):
+    """oracle port of the reference path on the host cores: fwd+bwd of the MLM loss on the first
+    `sample_B` samples of the C2 batch (fp32, padded layout exactly as the reference computes)."""
+    from oracle import encoder_oracle as orc
+    from uniter_b200.synth import seeded_state, synth_batch, uniter_state_shapes
+    torch.set_num_threads(os.cpu_count() or 1)
+    NL = args.layers
+    shapes = {"uniter." + k: v for k, v in uniter_state_shapes(BASE["H"], NL, BASE["I"], BASE["vocab"],
+                                                                BASE["max_pos"], 2, BASE["img_dim"]).items()}
+    shapes.update({"cls.predictions.transform.dense.weight": (BASE["H"], BASE["H"]),
+                   "cls.predictions.transform.dense.bias": (BASE["H"],),
+                   "cls.predictions.transform.LayerNorm.weight": (BASE["H"],),
+                   "cls.predictions.transform.LayerNorm.bias": (BASE["H"],),
+                   "cls.predictions.bias": (BASE["vocab"],)})
+    state = {k: v.requires_grad_(True) for k, v in seeded_state(shapes, seed=0).items()}
+    full = synth_batch(C2["B"], C2["tl"][0], C2["tl"][1], C2["nbb"][0], C2["nbb"][1], C2["seed"],
+                       mlm_prob=C2["mlm_prob"])
+    tl, nb = full["txt_lens"][:sample_B], full["num_bbs"][:sample_B]
+    batch = synth_batch(sample_B, 0, 0, 0, 0, C2["seed"], txt_lens=tl, num_bbs=nb, mlm_prob=C2["mlm_prob"])
+    times = []
+    for i in range(warmup + steps):
+        for v in state.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        loss = orc.mlm_forward(state, NL, BASE["heads"], batch).mean()
+        loss.backward()
+        times.append(time.perf_counter() - t0)
+    t = sum(times[warmup:]) / max(1, steps)
+    return dict(value=sample_B / t, ms_per_step=t * 1e3, cores=torch.get_num_threads(),
+                sample="first %d of the %d C2 samples (T=%d valid tokens), %d timed fwd+bwd steps, fp32"
+                       % (sample_B, C2["B"], sum(a + b for a, b in zip(tl, nb)), steps))
+
+
+# =============================================================================== our arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(args, max(1, min(args.steps, 3)), 1, args.cpu_sample)
+        line = {"metric": METRIC, "value": r["value"], "unit": "samples/s", "impl": "reference",
+                "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)), "warmup": 1,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "C2: UNITER-base %d-layer fwd+bwd + MLM head, CPU port of the "
+                                       "reference path, bounded sample" % args.layers,
+                           "global_batch": args.cpu_sample},
+                "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"],
+                                 "kind": "port", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from uniter_b200 import _lib
+    from uniter_b200.model import UniterConfig, register_lengths
+    from uniter_b200.heads import UniterForMLM
+    from uniter_b200.synth import synth_batch
+    from uniter_b200 import distributed as ubd
+
+    lib = _lib.load()
+    _lib.check(lib.ub200_device_check())
+    lib.ub200_launch_count.restype = C.c_ulonglong
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+    NL = args.layers
+
+    torch.manual_seed(0)
+    cfg = UniterConfig(BASE["vocab"], hidden_size=BASE["H"], num_hidden_layers=NL,
+                       num_attention_heads=BASE["heads"], intermediate_size=BASE["I"],
+                       max_position_embeddings=BASE["max_pos"])
+    model = UniterForMLM(cfg, BASE["img_dim"]).to(device=dev, dtype=dtype).train()
+    if world > 1:
+        ubd.broadcast_parameters(model, root=0)
+    reducer = ubd.GradientReducer(model) if world > 1 else None
+
+    # ---- synthetic batches (per-rank seed), host side pinned
+    n_host = 4
+    host = []
+    for i in range(n_host):
+        b = synth_batch(C2["B"], C2["tl"][0], C2["tl"][1], C2["nbb"][0], C2["nbb"][1],
+                        C2["seed"] + 1000 * rank + (i if i else 0), mlm_prob=C2["mlm_prob"])
+        hb = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()}
+        host.append(hb)
+    lens0 = [a + b for a, b in zip(host[0]["txt_lens"], host[0]["num_bbs"])]
+    tensor_keys = [k for k, v in host[0].items() if torch.is_tensor(v)]
+    h2d_bytes = sum(host[0][k].numel() * host[0][k].element_size() for k in tensor_keys)
+
+    def to_device(hb, stream=None):
+        with torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream()):
+            d = {k: hb[k].to(dev, non_blocking=True) for k in tensor_keys}
+        register_lengths(d["attn_masks"], [a + b for a, b in zip(hb["txt_lens"], hb["num_bbs"])])
+        return d
+
+    def step(batch):
+        model.zero_grad(set_to_none=True)
+        loss = model(batch).mean()
+        if reducer is not None:
+            reducer.backward_and_reduce(loss)
+        else:
+            loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    # ---- resident-input measurement ("value")
+    resident = to_device(host[0])
+    torch.cuda.synchronize()
+    for i in range(args.warmup):
+        step(resident)
+    torch.cuda.synchronize()
+    launches0 = lib.ub200_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(lambda i: step(resident), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (lib.ub200_launch_count() - launches0) // args.steps
+    ms_step = ms_total / args.steps
+    value = C2["B"] * world / (ms_step * 1e-3)
+
+    # ---- e2e: host batches from pinned memory, prefetched on a side stream, loss read back
+    copy_stream = torch.cuda.Stream()
+    state = {}
+
+    def prefetch(i):
+        hb = host[i % n_host]
+        copy_stream.wait_stream(torch.cuda.current_stream())
+        state["next"] = (to_device(hb, copy_stream), hb)
+
+    def e2e_step(i):
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        batch, _ = state["next"]
+        for t in batch.values():
+            t.record_stream(torch.cuda.current_stream())
+        prefetch(i + 1)
+        loss = step(batch)
+        state["loss"] = loss.detach().float().item()   # D2H read of the step's result
+
+    prefetch(0)
+    for i in range(min(3, args.warmup)):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    e2e_value = C2["B"] * world / (ms_e2e * 1e-3)
+
+    # ---- per-kernel-role pass (CUDA events around every launch on the launching stream)
+    breakdown, roofline = None, None
+    flops_step = algorithmic_flops(lens0, NL, BASE["H"])
+    pk = peaks()
+    if not args.no_profile:
+        NT = 24
+        lib.ub200_profile_enable(1)
+        psteps = 3
+        for i in range(psteps):
+            step(resident)
+        ms_arr = (C.c_float * NT)()
+        cnt_arr = (C.c_int * NT)()
+        _lib.check(lib.ub200_profile_collect(ms_arr, cnt_arr, NT))
+        lib.ub200_profile_enable(0)
+        names = {0: "gather/cvt", 1: "qkv_gemm", 2: "attn_fwd", 3: "attnout_gemm", 4: "ln1_fwd",
+                 5: "ffn1_gemm", 6: "ffn2_gemm", 7: "ln2_fwd", 8: "ln2_bwd", 9: "ffn2_dgrad",
+                 10: "ffn2_wgrad", 11: "ffn1_dgrad", 12: "ffn1_wgrad", 13: "ln1_bwd",
+                 14: "attnout_dgrad", 15: "attnout_wgrad", 16: "attn_bwd", 17: "colsum",
+                 18: "qkv_dgrad", 19: "qkv_wgrad", 20: "grad_add"}
+        breakdown = {names[i]: {"ms_per_step": round(ms_arr[i] / psteps, 4), "launches": cnt_arr[i] // psteps}
+                     for i in range(NT) if cnt_arr[i] > 0}
+        gemm_tags = [1, 3, 5, 6, 9, 10, 11, 12, 14, 15, 18, 19]
+        gemm_ms = sum(ms_arr[i] for i in gemm_tags) / psteps
+        gemm_launches = sum(cnt_arr[i] for i in gemm_tags) // psteps
+        T = sum(lens0)
+        gemm_flops = 3.0 * NL * 24.0 * BASE["H"] ** 2 * T          # dense-projection part of §8d
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": "ub::gemm_kernel (tcgen05, all 12 GEMM roles of a layer)",
+                    "achieved": round(achieved, 1), "peak": pk["tflops"], "unit": "TFLOP/s",
+                    "frac": round(achieved / pk["tflops"], 4), "peak_source": pk["source"],
+                    "launches_per_step": gemm_launches, "avg_launch_us": round(gemm_ms * 1e3 / max(1, gemm_launches), 2),
+                    "algorithmic_flops_per_step": gemm_flops, "traffic": None,
+                    "step_frac_of_peak": round(flops_step / (ms_step * 1e-3) / 1e12 / pk["tflops"], 4),
+                    "kernel_time_share_of_step": round(gemm_ms / ms_step, 3)}
+
+    # ---- CPU baseline (rank 0, N == 1 only): oracle port on the host cores, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(args, 2, 1, args.cpu_sample)
+        cpu = {"value": round(r["value"], 2), "unit": "samples/s", "cores": r["cores"], "kind": "port",
+               "sample": r["sample"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic",
+            "config": {"workload": "C2: UNITER-base %d-layer encoder fwd+bwd + MLM head (15%% text masked), "
+                                   "B=64 per GPU, varlen S~54 (rank-0 batch: T=%d valid tokens, max S=%d), "
+                                   "train mode dropout 0.1" % (NL, sum(lens0), max(lens0)),
+                       "global_batch": C2["B"] * world, "parallelism": "dp%d" % world,
+                       "l2": "per-step working set (weights 0.22 GB + saved activations ~1 GB) exceeds the "
+                             "126 MB L2; no explicit flush"},
+            "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "ms_per_step": round(ms_e2e, 4),
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "algorithmic_tflops_per_step": round(flops_step / 1e12, 4),
+            "achieved_tflops": round(flops_step / (ms_step * 1e-3) / 1e12, 1),
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "breakdown": breakdown,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,15 @@ int ub200_version(void);                      /* MAJOR*10000 + MINOR*100 + PATCH
 const char* ub200_last_error_string(void);    /* thread-local, never NULL */
 int ub200_device_check(void);                 /* 0 iff the current device is sm_100 (B200) */
 
+/* launch accounting / profiling (used by bench.py: "gpu_launches" and the roofline pass).
+ * Tags: 0 untagged (gather / convert), 1 qkv GEMM, 2 attention fwd, 3 attn-out GEMM, 4 LN1 fwd,
+ * 5 FFN1 GEMM, 6 FFN2 GEMM, 7 LN2 fwd, 8 LN2 bwd, 9 FFN2 dgrad, 10 FFN2 wgrad, 11 FFN1 dgrad,
+ * 12 FFN1 wgrad, 13 LN1 bwd, 14 attn-out dgrad, 15 attn-out wgrad, 16 attention bwd,
+ * 17 dbias column sum, 18 QKV dgrad, 19 QKV wgrad, 20 gradient add. */
+unsigned long long ub200_launch_count(void);  /* kernels launched by this library so far */
+int ub200_profile_enable(int on);
+int ub200_profile_collect(float* ms_per_tag, int* launches_per_tag, int ntags);
+
 /* ------------------------------------------------------------------------------------------
  * GEMM core:  D[M,N] = epilogue( sum_k A[m,k] * B[n,k] )      (tcgen05 + TMA, fp32 accumulate)
  *

@@ -155,6 +155,27 @@ def uniter_forward(state, num_layers, num_heads, input_ids, position_ids, img_fe
     return outs if output_all_encoded_layers else x
 
 
+def mlm_head(state, masked_hidden, prefix="cls.predictions."):
+    """model/layer.py:188-222 — LN(gelu(dense(h))) @ word_embeddings^T + bias (tied decoder,
+    model/pretrain.py:55-56)."""
+    h = layer_norm(gelu_erf(linear(masked_hidden, state[prefix + "transform.dense.weight"],
+                                   state[prefix + "transform.dense.bias"])),
+                   state[prefix + "transform.LayerNorm.weight"], state[prefix + "transform.LayerNorm.bias"])
+    return h @ state["uniter.embeddings.word_embeddings.weight"].t() + state[prefix + "bias"]
+
+
+def mlm_forward(state, num_layers, num_heads, batch):
+    """UniterForPretraining.forward_mlm (model/pretrain.py:107-133): per-masked-token CE loss."""
+    enc = {k[len("uniter."):]: v for k, v in state.items() if k.startswith("uniter.")}
+    seq = uniter_forward(enc, num_layers, num_heads, batch["input_ids"], batch["position_ids"],
+                         batch["img_feat"], batch["img_pos_feat"], batch["attn_masks"],
+                         batch["gather_index"], output_all_encoded_layers=False)
+    seq = seq[:, :batch["input_ids"].size(1), :]
+    mask = batch["txt_labels"] != -1
+    scores = mlm_head(state, seq[mask])
+    return torch.nn.functional.cross_entropy(scores, batch["txt_labels"][mask], reduction="none")
+
+
 # ----------------------------------------------------------------------------- host-side index logic
 def get_gather_index(txt_lens, num_bbs, batch_size, max_len, out_size):
     """data/data.py:271-279 — canonical compaction index (pure integer logic)."""

@@ -69,9 +69,56 @@ int make_tma_2d(CUtensorMap* out, const void* base, int dtype, uint64_t rows, ui
   return 0;
 }
 
+
+thread_local int g_prof_tag = 0;
+static bool g_prof_on = false;
+static unsigned long long g_launches = 0;
+struct ProfRec { int tag; cudaEvent_t e0, e1; };
+static ProfRec g_recs[8192];
+static int g_nrec = 0;
+
+ProfScope::ProfScope(cudaStream_t s) : stream(s), slot(-1) {
+  ++g_launches;
+  if (g_prof_on && g_nrec < 8192) {
+    slot = g_nrec++;
+    ProfRec& r = g_recs[slot];
+    r.tag = g_prof_tag;
+    if (!r.e0) { cudaEventCreate(&r.e0); cudaEventCreate(&r.e1); }
+    cudaEventRecord(r.e0, stream);
+  }
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_recs[slot].e1, stream);
+}
+
 }  // namespace ub
 
 extern "C" {
+
+unsigned long long ub200_launch_count(void) { return ub::g_launches; }
+
+int ub200_profile_enable(int on) {
+  ub::g_prof_on = on != 0;
+  if (on) ub::g_nrec = 0;
+  return 0;
+}
+
+// Synchronises the device, sums the recorded launch durations per tag (ms) and launch counts
+// per tag into ms_out[ntags] / count_out[ntags]; clears the record list.
+int ub200_profile_collect(float* ms_out, int* count_out, int ntags) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return ub::set_error(UB200_ECUDA, "profile_collect: %s", cudaGetErrorString(e));
+  for (int i = 0; i < ntags; ++i) { ms_out[i] = 0.f; count_out[i] = 0; }
+  for (int i = 0; i < ub::g_nrec; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ub::g_recs[i].e0, ub::g_recs[i].e1);
+    const int t = ub::g_recs[i].tag;
+    if (t >= 0 && t < ntags) { ms_out[t] += ms; count_out[t] += 1; }
+  }
+  ub::g_nrec = 0;
+  return 0;
+}
+
 
 int ub200_version(void) { return 100; /* 0.1.0 */ }
 

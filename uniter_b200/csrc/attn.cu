@@ -585,6 +585,7 @@ extern "C" int ub200_attn_fwd(const ub200_attn_args* args, ub200_stream_t stream
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
       configured[1] = true;
     }
+    ProfScope ps(stream);
     attn_fwd_kernel<true><<<grid, 128, ATT_FWD_SMEM, stream>>>(tm, p);
   } else {
     if (!configured[0]) {
@@ -592,6 +593,7 @@ extern "C" int ub200_attn_fwd(const ub200_attn_args* args, ub200_stream_t stream
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
       configured[0] = true;
     }
+    ProfScope ps(stream);
     attn_fwd_kernel<false><<<grid, 128, ATT_FWD_SMEM, stream>>>(tm, p);
   }
   UB_CHECK_CUDA(cudaGetLastError());
@@ -655,10 +657,14 @@ extern "C" int ub200_attn_bwd(const ub200_attn_args* args, ub200_stream_t stream
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
     configured[di] = true;
   }
-  if (di) attn_bwd_kernel<true><<<grid, 128, ATT_BWD_SMEM, stream>>>(tmQ, tmD, p, acc);
-  else attn_bwd_kernel<false><<<grid, 128, ATT_BWD_SMEM, stream>>>(tmQ, tmD, p, acc);
+  {
+    ProfScope ps(stream);
+    if (di) attn_bwd_kernel<true><<<grid, 128, ATT_BWD_SMEM, stream>>>(tmQ, tmD, p, acc);
+    else attn_bwd_kernel<false><<<grid, 128, ATT_BWD_SMEM, stream>>>(tmQ, tmD, p, acc);
+  }
   UB_CHECK_CUDA(cudaGetLastError());
   if (multi) {
+    ProfScope ps(stream);
     if (di) attn_dq_convert_kernel<true><<<a.batch, 256, 0, stream>>>(acc, a.dqkv, a.cu_seqlens, a.hidden);
     else attn_dq_convert_kernel<false><<<a.batch, 256, 0, stream>>>(acc, a.dqkv, a.cu_seqlens, a.hidden);
     UB_CHECK_CUDA(cudaGetLastError());

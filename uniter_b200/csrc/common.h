@@ -30,4 +30,22 @@ int num_sms();  // SM count of the current device (cached)
 int make_tma_2d(CUtensorMap* out, const void* base, int dtype, uint64_t rows, uint64_t cols,
                 uint64_t ld, uint32_t box_rows, uint32_t box_cols);
 
+
+// Launch accounting + optional per-launch CUDA-event timing (bench.py's roofline pass).
+// Every kernel launch site constructs a ProfScope right before the <<<>>>; it always counts the
+// launch, and when profiling is enabled brackets it with a cudaEvent pair tagged with the
+// role set by the caller (g_prof_tag, e.g. "FFN1 forward GEMM").
+extern thread_local int g_prof_tag;
+struct ProfScope {
+  explicit ProfScope(cudaStream_t s);
+  ~ProfScope();
+  cudaStream_t stream;
+  int slot;
+};
+struct ProfTag {
+  explicit ProfTag(int t) : prev(g_prof_tag) { g_prof_tag = t; }
+  ~ProfTag() { g_prof_tag = prev; }
+  int prev;
+};
+
 }  // namespace ub

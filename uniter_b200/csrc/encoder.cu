@@ -131,7 +131,10 @@ extern "C" int ub200_encoder_fwd(const ub200_encoder_desc* d, const ub200_layer_
     ub200_gemm_args g = gemm_base(d);
     g.a = x; g.lda = H; g.b = w.wqkv; g.ldb = H; g.M = T; g.N = 3 * H; g.K = H;
     g.epilogue = UB200_EPI_BIAS; g.bias = w.bqkv; g.out = A + L.qkv; g.ldo = 3 * H;
-    UB_TRY(ub200_gemm(&g, stream));
+    {
+      ProfTag _t(1);
+      UB_TRY(ub200_gemm(&g, stream));
+    }
 
     // ctx = softmax(q k^T / 8 [keys of the same sequence]) v   model/layer.py:80-100
     ub200_attn_args at{};
@@ -140,7 +143,10 @@ extern "C" int ub200_encoder_fwd(const ub200_encoder_desc* d, const ub200_layer_
     at.max_seqlen = d->max_seqlen; at.hidden = H; at.num_heads = d->num_heads; at.dtype = d->dtype;
     at.dropout_p = d->attn_dropout_p; at.rng_seed = d->rng_seed;
     at.rng_stream = rng_stream_of(d, l, SITE_ATTN_PROBS);
-    UB_TRY(ub200_attn_fwd(&at, stream));
+    {
+      ProfTag _t(2);
+      UB_TRY(ub200_attn_fwd(&at, stream));
+    }
 
     // s1 = dropout(ctx Wo^T + bo) + x                          model/layer.py:112-114
     g = gemm_base(d);
@@ -148,17 +154,26 @@ extern "C" int ub200_encoder_fwd(const ub200_encoder_desc* d, const ub200_layer_
     g.epilogue = UB200_EPI_BIAS | UB200_EPI_RESIDUAL | (d->hidden_dropout_p > 0 ? UB200_EPI_DROPOUT : 0);
     g.bias = w.bo; g.residual = x; g.ldr = H; g.out = A + L.s1; g.ldo = H;
     g.dropout_p = d->hidden_dropout_p; g.rng_stream = rng_stream_of(d, l, SITE_ATTN_OUT);
-    UB_TRY(ub200_gemm(&g, stream));
+    {
+      ProfTag _t(3);
+      UB_TRY(ub200_gemm(&g, stream));
+    }
 
     // a = LayerNorm(s1)                                        model/layer.py:114
-    UB_TRY(ub200_layernorm_fwd(A + L.s1, w.ln1_g, w.ln1_b, A + L.a, T, H, d->dtype, stream));
+    {
+      ProfTag _t(4);
+      UB_TRY(ub200_layernorm_fwd(A + L.s1, w.ln1_g, w.ln1_b, A + L.a, T, H, d->dtype, stream));
+    }
 
     // pre = a W1^T + b1 ; f = gelu(pre)                        model/layer.py:140-141, :31-37
     g = gemm_base(d);
     g.a = A + L.a; g.lda = H; g.b = w.w1; g.ldb = H; g.M = T; g.N = I; g.K = H;
     g.epilogue = UB200_EPI_BIAS | UB200_EPI_GELU;
     g.bias = w.b1; g.out = A + L.f; g.out2 = A + L.pre; g.ldo = I;
-    UB_TRY(ub200_gemm(&g, stream));
+    {
+      ProfTag _t(5);
+      UB_TRY(ub200_gemm(&g, stream));
+    }
 
     // s2 = dropout(f W2^T + b2) + a                            model/layer.py:153-155
     g = gemm_base(d);
@@ -166,10 +181,16 @@ extern "C" int ub200_encoder_fwd(const ub200_encoder_desc* d, const ub200_layer_
     g.epilogue = UB200_EPI_BIAS | UB200_EPI_RESIDUAL | (d->hidden_dropout_p > 0 ? UB200_EPI_DROPOUT : 0);
     g.bias = w.b2; g.residual = A + L.a; g.ldr = H; g.out = A + L.s2; g.ldo = H;
     g.dropout_p = d->hidden_dropout_p; g.rng_stream = rng_stream_of(d, l, SITE_FFN_OUT);
-    UB_TRY(ub200_gemm(&g, stream));
+    {
+      ProfTag _t(6);
+      UB_TRY(ub200_gemm(&g, stream));
+    }
 
     // out = LayerNorm(s2)                                      model/layer.py:155
-    UB_TRY(ub200_layernorm_fwd(A + L.s2, w.ln2_g, w.ln2_b, layer_out[l], T, H, d->dtype, stream));
+    {
+      ProfTag _t(7);
+      UB_TRY(ub200_layernorm_fwd(A + L.s2, w.ln2_g, w.ln2_b, layer_out[l], T, H, d->dtype, stream));
+    }
     x = layer_out[l];
   }
   return 0;
@@ -219,7 +240,10 @@ extern "C" int ub200_encoder_bwd(const ub200_encoder_desc* d, const ub200_layer_
     ln.dgamma = gr.small + SG.dg2; ln.dbeta = gr.small + SG.db2ln; ln.dbias = gr.small + SG.db2;
     ln.rows = T; ln.hidden = H; ln.dtype = d->dtype; ln.dropout_p = d->hidden_dropout_p;
     ln.rng_seed = d->rng_seed; ln.rng_stream = rng_stream_of(d, l, SITE_FFN_OUT);
-    UB_TRY(ub200_layernorm_bwd(&ln, stream));
+    {
+      ProfTag _t(8);
+      UB_TRY(ub200_layernorm_bwd(&ln, stream));
+    }
     const void* dy2 = drop ? sc + S.bufB : sc + S.bufA;
 
     // ---- dPre = (dY2 W2) o gelu'(pre) ; db1 = colsum(dPre)
@@ -227,22 +251,34 @@ extern "C" int ub200_encoder_bwd(const ub200_encoder_desc* d, const ub200_layer_
     g.a = dy2; g.lda = H; g.b = w.w2; g.ldb = I; g.b_major = 1; g.M = T; g.N = I; g.K = H;
     g.epilogue = UB200_EPI_DGELU | UB200_EPI_COLSUM; g.aux = A + L.pre; g.ldaux = I;
     g.colsum = gr.small + SG.db1; g.out = sc + S.dpre; g.ldo = I;
-    UB_TRY(ub200_gemm(&g, stream));
+    {
+      ProfTag _t(9);
+      UB_TRY(ub200_gemm(&g, stream));
+    }
     // ---- dW2[H, I] = dY2^T f
     g = gemm_base(d);
     g.a = dy2; g.lda = H; g.a_major = 1; g.b = A + L.f; g.ldb = I; g.b_major = 1;
     g.M = H; g.N = I; g.K = T; g.epilogue = acc; g.out = gr.dw2; g.ldo = I;
-    UB_TRY(ub200_gemm(&g, stream));
+    {
+      ProfTag _t(10);
+      UB_TRY(ub200_gemm(&g, stream));
+    }
     // ---- da = dPre W1 + ds2   (bufC)
     g = gemm_base(d);
     g.a = sc + S.dpre; g.lda = I; g.b = w.w1; g.ldb = H; g.b_major = 1; g.M = T; g.N = H; g.K = I;
     g.epilogue = UB200_EPI_RESIDUAL; g.residual = sc + S.bufA; g.ldr = H; g.out = sc + S.bufC; g.ldo = H;
-    UB_TRY(ub200_gemm(&g, stream));
+    {
+      ProfTag _t(11);
+      UB_TRY(ub200_gemm(&g, stream));
+    }
     // ---- dW1[I, H] = dPre^T a
     g = gemm_base(d);
     g.a = sc + S.dpre; g.lda = I; g.a_major = 1; g.b = A + L.a; g.ldb = H; g.b_major = 1;
     g.M = I; g.N = H; g.K = T; g.epilogue = acc; g.out = gr.dw1; g.ldo = H;
-    UB_TRY(ub200_gemm(&g, stream));
+    {
+      ProfTag _t(12);
+      UB_TRY(ub200_gemm(&g, stream));
+    }
 
     // ---- a = LN(s1): ds1 (bufA), masked copy (bufB), dgamma/dbeta, dbo
     ln = ub200_ln_bwd_args{};
@@ -251,19 +287,28 @@ extern "C" int ub200_encoder_bwd(const ub200_encoder_desc* d, const ub200_layer_
     ln.dgamma = gr.small + SG.dg1; ln.dbeta = gr.small + SG.db1ln; ln.dbias = gr.small + SG.dbo;
     ln.rows = T; ln.hidden = H; ln.dtype = d->dtype; ln.dropout_p = d->hidden_dropout_p;
     ln.rng_seed = d->rng_seed; ln.rng_stream = rng_stream_of(d, l, SITE_ATTN_OUT);
-    UB_TRY(ub200_layernorm_bwd(&ln, stream));
+    {
+      ProfTag _t(13);
+      UB_TRY(ub200_layernorm_bwd(&ln, stream));
+    }
     const void* dy1 = drop ? sc + S.bufB : sc + S.bufA;
 
     // ---- dctx = dY1 Wo   (bufC)
     g = gemm_base(d);
     g.a = dy1; g.lda = H; g.b = w.wo; g.ldb = H; g.b_major = 1; g.M = T; g.N = H; g.K = H;
     g.out = sc + S.bufC; g.ldo = H;
-    UB_TRY(ub200_gemm(&g, stream));
+    {
+      ProfTag _t(14);
+      UB_TRY(ub200_gemm(&g, stream));
+    }
     // ---- dWo[H, H] = dY1^T ctx
     g = gemm_base(d);
     g.a = dy1; g.lda = H; g.a_major = 1; g.b = A + L.ctx; g.ldb = H; g.b_major = 1;
     g.M = H; g.N = H; g.K = T; g.epilogue = acc; g.out = gr.dwo; g.ldo = H;
-    UB_TRY(ub200_gemm(&g, stream));
+    {
+      ProfTag _t(15);
+      UB_TRY(ub200_gemm(&g, stream));
+    }
 
     // ---- attention backward: dqkv
     ub200_attn_args at{};
@@ -274,23 +319,38 @@ extern "C" int ub200_encoder_bwd(const ub200_encoder_desc* d, const ub200_layer_
     at.dropout_p = d->attn_dropout_p; at.rng_seed = d->rng_seed;
     at.rng_stream = rng_stream_of(d, l, SITE_ATTN_PROBS);
     at.dctx = sc + S.bufC; at.dqkv = sc + S.dqkv; at.workspace = attn_ws ? sc + S.attn_ws : nullptr;
-    UB_TRY(ub200_attn_bwd(&at, stream));
+    {
+      ProfTag _t(16);
+      UB_TRY(ub200_attn_bwd(&at, stream));
+    }
     // ---- dbqkv = colsum(dqkv)
-    UB_TRY(ub200_colsum(sc + S.dqkv, gr.small + SG.dbqkv, T, 3 * H, 3 * H, d->dtype, stream));
+    {
+      ProfTag _t(17);
+      UB_TRY(ub200_colsum(sc + S.dqkv, gr.small + SG.dbqkv, T, 3 * H, 3 * H, d->dtype, stream));
+    }
     // ---- dx = dqkv Wqkv + ds1  -> gradient wrt the layer input
     g = gemm_base(d);
     g.a = sc + S.dqkv; g.lda = 3 * H; g.b = w.wqkv; g.ldb = H; g.b_major = 1; g.M = T; g.N = H; g.K = 3 * H;
     g.epilogue = UB200_EPI_RESIDUAL; g.residual = sc + S.bufA; g.ldr = H; g.out = dnext; g.ldo = H;
-    UB_TRY(ub200_gemm(&g, stream));
+    {
+      ProfTag _t(18);
+      UB_TRY(ub200_gemm(&g, stream));
+    }
     // ---- dWqkv[3H, H] = dqkv^T x
     g = gemm_base(d);
     g.a = sc + S.dqkv; g.lda = 3 * H; g.a_major = 1; g.b = x; g.ldb = H; g.b_major = 1;
     g.M = 3 * H; g.N = H; g.K = T; g.epilogue = acc; g.out = gr.dwqkv; g.ldo = H;
-    UB_TRY(ub200_gemm(&g, stream));
+    {
+      ProfTag _t(19);
+      UB_TRY(ub200_gemm(&g, stream));
+    }
 
     // gradient flowing into the previous layer's output (+ its external gradient, if any)
     if (l > 0 && d_layer_out[l - 1]) {
+      {
+      ProfTag _t(20);
       UB_TRY(launch_add16(d->dtype, dnext, dnext, d_layer_out[l - 1], static_cast<long long>(T) * H, cs));
+    }
     }
     dcur = dnext;
   }

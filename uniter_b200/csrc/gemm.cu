@@ -327,7 +327,10 @@ static int launch_gemm(const ub200_gemm_args& a, const GemmParams& p, const CUte
                                        Cfg::SMEM_BYTES));
     configured = true;
   }
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  {
+    ProfScope ps(stream);
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  }
   UB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -312,6 +312,7 @@ int launch_ln_fwd(int dtype, const void* x, const void* gamma, const void* beta,
     return set_error(UB200_EUNSUPPORTED, "ln_fwd: need rows > 0, H %% 8 == 0 and H <= %d (H=%d)",
                      LN_MAX_VEC * 256, H);
   const int grid = (rows + 7) / 8;
+  ProfScope ps(stream);
   if (dtype == UB200_BF16) ln_fwd_kernel<true><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, H);
   else ln_fwd_kernel<false><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, H);
   UB_CHECK_CUDA(cudaGetLastError());
@@ -325,6 +326,7 @@ int launch_ln_bwd(int dtype, const LnBwdParams& p, cudaStream_t stream) {
   int grid = (p.rows + 7) / 8;
   const int cap = num_sms() * 2;
   if (grid > cap) grid = cap;
+  ProfScope ps(stream);
   if (dtype == UB200_BF16) ln_bwd_kernel<true><<<grid, 256, 0, stream>>>(p);
   else ln_bwd_kernel<false><<<grid, 256, 0, stream>>>(p);
   UB_CHECK_CUDA(cudaGetLastError());
@@ -335,6 +337,7 @@ int launch_gather_rows(const void* src, void* dst, const int* idx, int rows, int
                        cudaStream_t stream) {
   if (row_bytes % 16 != 0 || rows <= 0)
     return set_error(UB200_EINVAL, "gather_rows: rows > 0 and row_bytes %% 16 == 0 required");
+  ProfScope ps(stream);
   gather_rows_kernel<0><<<(rows + 7) / 8, 256, 0, stream>>>(
       reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), idx, rows, row_bytes / 16);
   UB_CHECK_CUDA(cudaGetLastError());
@@ -350,6 +353,7 @@ int launch_colsum(int dtype, const void* x, float* out, int rows, int N, int ld,
   if (gy < 1) gy = 1;
   const int rpc = (rows + gy - 1) / gy;
   dim3 grid(gx, gy);
+  ProfScope ps(stream);
   if (dtype == UB200_BF16) colsum_kernel<true><<<grid, 256, 0, stream>>>(x, out, rows, N, ld, rpc);
   else colsum_kernel<false><<<grid, 256, 0, stream>>>(x, out, rows, N, ld, rpc);
   UB_CHECK_CUDA(cudaGetLastError());
@@ -362,6 +366,7 @@ int launch_cvt(int dtype, const float* src, void* dst, long long n, int accumula
   long long blocks = (n + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 8;
   if (blocks > cap) blocks = cap;
+  ProfScope ps(stream);
   if (dtype == UB200_BF16)
     cvt_kernel<true><<<static_cast<int>(blocks), 256, 0, stream>>>(src, dst, n, accumulate);
   else
@@ -377,6 +382,7 @@ int launch_add16(int dtype, void* dst, const void* a, const void* b, long long n
   const long long cap = static_cast<long long>(num_sms()) * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
+  ProfScope ps(stream);
   if (dtype == UB200_BF16)
     add16_kernel<true><<<static_cast<int>(blocks), 256, 0, stream>>>(
         reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(a),
