@@ -17,21 +17,22 @@ def _close(got, ref, tol, what):
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("shape", [(128, 128, 64), (333, 768, 768), (3451, 2304, 768), (777, 768, 3072),
                                    (1, 64, 64), (130, 8, 72)])
-@pytest.mark.parametrize("tn", [0, 64, 128, 256])
-def test_gemm_operand_majors(dtype, shape, tn):
+@pytest.mark.parametrize("tn,cluster", [(0, 0), (64, 1), (128, 1), (256, 1), (128, 2), (256, 2)])
+def test_gemm_operand_majors(dtype, shape, tn, cluster):
     from uniter_b200 import ops
     M, N, K = shape
     torch.manual_seed(M * 7 + N)
     x = torch.randn(M, K, device="cuda").to(dtype)
     w = (torch.randn(N, K, device="cuda") * 0.05).to(dtype)
     ref = x.float() @ w.float().t()
-    _close(ops.gemm(x, w, tile_n=tn), ref, TOL[dtype], "K-major x K-major")
+    _close(ops.gemm(x, w, tile_n=tn, cluster=cluster), ref, TOL[dtype], "K-major x K-major")
     wt = w.t().contiguous()
-    _close(ops.gemm(x, wt, b_major=1, tile_n=tn), ref, TOL[dtype], "K-major x MN-major (dgrad form)")
+    _close(ops.gemm(x, wt, b_major=1, tile_n=tn, cluster=cluster), ref, TOL[dtype],
+           "K-major x MN-major (dgrad form)")
     Mp = (M + 7) // 8 * 8
     xt = torch.zeros(K, Mp, device="cuda", dtype=dtype)[:, :M]
     xt.copy_(x.t())
-    _close(ops.gemm(xt, wt, a_major=1, b_major=1, tile_n=tn), ref, TOL[dtype],
+    _close(ops.gemm(xt, wt, a_major=1, b_major=1, tile_n=tn, cluster=cluster), ref, TOL[dtype],
            "MN-major x MN-major (wgrad form)")
 
 

@@ -118,34 +118,42 @@ def main():
               % (dropped, same, diff, err), flush=True)
         all_ok &= abs(dropped - 0.1) < 0.01 and same and diff > 0.1 and err < tol * 10
 
-    # timing of the four forward GEMM shapes at C2 (T=3451)
-    for (M, N, K) in ((3451, 2304, 768), (3451, 768, 768), (3451, 3072, 768), (3451, 768, 3072)):
-        x = torch.randn(M, K, device=dev).to(torch.bfloat16)
-        w = torch.randn(N, K, device=dev).to(torch.bfloat16)
-        for tn in (64, 128, 256):
-            for _ in range(3):
-                ops.gemm(x, w, tile_n=tn)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-            e0.record()
-            for _ in range(20):
-                ops.gemm(x, w, tile_n=tn)
-            e1.record()
-            torch.cuda.synchronize()
-            us = e0.elapsed_time(e1) / 20 * 1e3
-            print("time %dx%dx%d tn=%d: %.1f us  %.1f TFLOP/s" % (M, N, K, tn, us, 2.0 * M * N * K / us / 1e6),
-                  flush=True)
-        for _ in range(3):
-            x @ w.t()
+    # timing of the forward / dgrad / wgrad GEMM shapes at C2 (T=3451)
+    def tm(fn, n=30):
+        for _ in range(5):
+            fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         e0.record()
-        for _ in range(20):
-            x @ w.t()
+        for _ in range(n):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) / 20 * 1e3
-        print("time %dx%dx%d cublas: %.1f us  %.1f TFLOP/s" % (M, N, K, us, 2.0 * M * N * K / us / 1e6), flush=True)
+        return e0.elapsed_time(e1) / n * 1e3
+    T = 3451
+    for (M, N, K, am, bm, what) in ((T, 2304, 768, 0, 0, "qkv fwd"), (T, 768, 768, 0, 0, "attnout fwd"),
+                                    (T, 3072, 768, 0, 0, "ffn1 fwd"), (T, 768, 3072, 0, 0, "ffn2 fwd"),
+                                    (T, 3072, 768, 0, 1, "ffn2 dgrad"), (T, 768, 3072, 0, 1, "ffn1 dgrad"),
+                                    (768, 3072, T, 1, 1, "ffn2 wgrad"), (3072, 768, T, 1, 1, "ffn1 wgrad"),
+                                    (768, 768, T, 1, 1, "attnout wgrad"), (2304, 768, T, 1, 1, "qkv wgrad")):
+        a = torch.randn((K, M) if am else (M, K), device=dev).to(torch.bfloat16)
+        b = torch.randn((K, N) if bm else (N, K), device=dev).to(torch.bfloat16)
+        res = []
+        for tn, cl in ((0, 0), (64, 1), (128, 1), (256, 1), (128, 2), (256, 2)):
+            us = tm(lambda: ops.gemm(a, b, a_major=am, b_major=bm, tile_n=tn, cluster=cl))
+            res.append("tn%d/c%d %.1fus %.0fTF" % (tn, cl, us, 2.0 * M * N * K / us / 1e6))
+        aa = a.t() if am else a
+        bb = b if bm else b.t()
+        us = tm(lambda: aa @ bb)
+        print("time %-14s %dx%dx%d: %s | cublas %.1fus %.0fTF" % (what, M, N, K, "  ".join(res), us,
+                                                              2.0 * M * N * K / us / 1e6), flush=True)
+    # epilogue cost: ffn1 with GELU, ffn2 dgrad with dGELU + colsum
+    x = torch.randn(T, 768, device=dev).bfloat16(); w = torch.randn(3072, 768, device=dev).bfloat16()
+    bias = torch.randn(3072, device=dev).bfloat16()
+    print("ffn1 gelu epilogue: %.1f us" % tm(lambda: ops.gemm(x, w, bias=bias, gelu=True)), flush=True)
+    dy = torch.randn(T, 768, device=dev).bfloat16(); w2 = torch.randn(768, 3072, device=dev).bfloat16()
+    pre = torch.randn(T, 3072, device=dev).bfloat16(); cs = torch.zeros(3072, device=dev)
+    print("ffn2 dgrad dgelu+colsum epilogue: %.1f us" % tm(lambda: ops.gemm(dy, w2, b_major=1, aux=pre, dgelu=True, colsum=cs)), flush=True)
     print("ALL_OK" if all_ok else "SOME_FAILED", flush=True)
 
 

@@ -26,7 +26,7 @@ class GemmArgs(C.Structure):
         ("ldr", C.c_int64), ("ldaux", C.c_int64), ("ldo", C.c_int64),
         ("dropout_p", C.c_float),
         ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64),
-        ("tile_n", C.c_int32), ("max_ctas", C.c_int32),
+        ("tile_n", C.c_int32), ("max_ctas", C.c_int32), ("cluster", C.c_int32),
     ]
 
 

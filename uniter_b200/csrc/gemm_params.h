@@ -1,0 +1,26 @@
+// Shared between the GEMM device code (gemm_impl.cuh) and its C entry point (gemm.cu).
+#pragma once
+#include <stdint.h>
+
+namespace ub {
+
+constexpr int BM = 128;   // accumulator rows per CTA == TMEM lanes
+constexpr int BK = 64;    // 64 x 16-bit = one 128-byte swizzle row
+
+struct GemmParams {
+  int M, N, K;
+  int epilogue;
+  const void* bias;
+  const void* residual;
+  const void* aux;
+  void* out;
+  void* out2;
+  float* colsum;
+  long long ldr, ldaux, ldo;
+  uint32_t drop_thr16;
+  float drop_inv_keep;
+  uint32_t seed_lo, seed_hi, stream_lo, stream_hi;
+  int tiles_m, tiles_n;
+};
+
+}  // namespace ub

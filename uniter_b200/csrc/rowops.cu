@@ -103,7 +103,10 @@ struct LnBwdParams {
   uint32_t seed_lo, seed_hi, stream_lo, stream_hi;
 };
 
-template <bool kBF16>
+// NV = vectors (8 columns) per lane = ceil(H / 256): register arrays are sized for the actual
+// hidden size (H = 768 -> 3), and the next row's x / dy are prefetched while the current row is
+// reduced, so one wave of one CTA per SM covers the whole [T, H] matrix.
+template <bool kBF16, int NV>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const LnBwdParams p) {
   using T16 = typename Elem<kBF16>::T;
@@ -111,48 +114,72 @@ ln_bwd_kernel(const LnBwdParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
   const int H = p.H, nvec = H >> 3;
-  float gam[LN_MAX_VEC][8];
-  float acc_g[LN_MAX_VEC][8], acc_b[LN_MAX_VEC][8], acc_d[LN_MAX_VEC][8];
+  float gam[NV][8];
+  float acc_g[NV][8], acc_b[NV][8], acc_d[NV][8];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int vi = lane + i * 32;
-    if (vi < nvec) unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(p.gamma) + vi), gam[i]);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { acc_g[i][e] = 0.f; acc_b[i][e] = 0.f; acc_d[i][e] = 0.f; }
+    for (int e = 0; e < 8; ++e) { gam[i][e] = 0.f; acc_g[i][e] = 0.f; acc_b[i][e] = 0.f; acc_d[i][e] = 0.f; }
+    if (vi < nvec) unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(p.gamma) + vi), gam[i]);
   }
   DropoutRng rng;
   rng.k0 = p.seed_lo; rng.k1 = p.seed_hi; rng.s0 = p.stream_lo; rng.s1 = p.stream_hi;
   rng.thr16 = p.drop_thr16; rng.inv_keep = p.drop_inv_keep;
+  const float inv_h = 1.0f / H;
 
-  for (int row = blockIdx.x * nwarps + warp; row < p.rows; row += gridDim.x * nwarps) {
-    const uint4* xr = reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(p.x) +
-                                                     static_cast<size_t>(row) * H);
-    const uint4* dyr = reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(p.dy) +
-                                                      static_cast<size_t>(row) * H);
-    float xv[LN_MAX_VEC][8], dv[LN_MAX_VEC][8];
-    float sum = 0.f;
+  const int stride = gridDim.x * nwarps;
+  int row = blockIdx.x * nwarps + warp;
+  uint4 nx[NV], nd[NV];
+  if (row < p.rows) {
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
-        unpack8<kBF16>(__ldg(xr + vi), xv[i]);
-        unpack8<kBF16>(__ldg(dyr + vi), dv[i]);
+        nx[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(p.x) +
+                                                     static_cast<size_t>(row) * H) + vi);
+        nd[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(p.dy) +
+                                                     static_cast<size_t>(row) * H) + vi);
+      }
+    }
+  }
+  for (; row < p.rows; row += stride) {
+    float xv[NV][8], dv[NV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + i * 32 < nvec) {
+        unpack8<kBF16>(nx[i], xv[i]);
+        unpack8<kBF16>(nd[i], dv[i]);
 #pragma unroll
         for (int e = 0; e < 8; ++e) sum += xv[i][e];
       }
     }
-    const float mean = warp_sum(sum) / H;
+    const int nrow = row + stride;   // prefetch the next row of this warp
+    if (nrow < p.rows) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) {
+          nx[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(p.x) +
+                                                       static_cast<size_t>(nrow) * H) + vi);
+          nd[i] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(p.dy) +
+                                                       static_cast<size_t>(nrow) * H) + vi);
+        }
+      }
+    }
+    const float mean = warp_sum(sum) * inv_h;
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i)
+    for (int i = 0; i < NV; ++i)
       if (lane + i * 32 < nvec) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) { const float d = xv[i][e] - mean; sq += d * d; }
       }
-    const float rstd = rsqrtf(warp_sum(sq) / H + LN_EPS);
+    const float rstd = rsqrtf(warp_sum(sq) * inv_h + LN_EPS);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i)
+    for (int i = 0; i < NV; ++i)
       if (lane + i * 32 < nvec) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -165,14 +192,14 @@ ln_bwd_kernel(const LnBwdParams p) {
           dv[i][e] = g;            // keep dy * gamma
         }
       }
-    s1 = warp_sum(s1) / H;
-    s2 = warp_sum(s2) / H;
+    s1 = warp_sum(s1) * inv_h;
+    s2 = warp_sum(s2) * inv_h;
     uint4* dxr = reinterpret_cast<uint4*>(reinterpret_cast<T16*>(p.dx) + static_cast<size_t>(row) * H);
     uint4* ddr = p.dx_drop ? reinterpret_cast<uint4*>(reinterpret_cast<T16*>(p.dx_drop) +
                                                       static_cast<size_t>(row) * H)
                            : nullptr;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
         float o[8];
@@ -198,7 +225,7 @@ ln_bwd_kernel(const LnBwdParams p) {
 
   // CTA reduction over warps, one vector slot at a time, then one atomic per column per CTA
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -207,9 +234,8 @@ ln_bwd_kernel(const LnBwdParams p) {
       red[2][warp][lane * 8 + e] = acc_d[i][e];
     }
     __syncthreads();
-    // 256 threads <-> 256 columns of this slot
-    const int colslot = threadIdx.x;            // lane*8 + e
-    const int col = (colslot >> 3) * 8 + (colslot & 7) + i * 256;
+    const int colslot = threadIdx.x;  // 256 threads <-> the 256 columns of this slot
+    const int col = colslot + i * 256;
     if (col < H) {
       float a = 0.f, b = 0.f, d = 0.f;
       for (int w = 0; w < nwarps; ++w) {
@@ -319,16 +345,27 @@ int launch_ln_fwd(int dtype, const void* x, const void* gamma, const void* beta,
   return 0;
 }
 
+template <bool kBF16>
+static void launch_ln_bwd_nv(const LnBwdParams& p, int grid, cudaStream_t stream) {
+  const int nv = (p.H + 255) / 256;
+  switch (nv) {
+    case 1: ln_bwd_kernel<kBF16, 1><<<grid, 256, 0, stream>>>(p); break;
+    case 2: ln_bwd_kernel<kBF16, 2><<<grid, 256, 0, stream>>>(p); break;
+    case 3: ln_bwd_kernel<kBF16, 3><<<grid, 256, 0, stream>>>(p); break;
+    default: ln_bwd_kernel<kBF16, 4><<<grid, 256, 0, stream>>>(p); break;
+  }
+}
+
 int launch_ln_bwd(int dtype, const LnBwdParams& p, cudaStream_t stream) {
   if (p.H % 8 != 0 || p.H > LN_MAX_VEC * 256 || p.rows <= 0)
     return set_error(UB200_EUNSUPPORTED, "ln_bwd: need rows > 0, H %% 8 == 0 and H <= %d (H=%d)",
                      LN_MAX_VEC * 256, p.H);
   int grid = (p.rows + 7) / 8;
-  const int cap = num_sms() * 2;
+  const int cap = num_sms();   // one wave, one CTA per SM
   if (grid > cap) grid = cap;
   ProfScope ps(stream);
-  if (dtype == UB200_BF16) ln_bwd_kernel<true><<<grid, 256, 0, stream>>>(p);
-  else ln_bwd_kernel<false><<<grid, 256, 0, stream>>>(p);
+  if (dtype == UB200_BF16) launch_ln_bwd_nv<true>(p, grid, stream);
+  else launch_ln_bwd_nv<false>(p, grid, stream);
   UB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -14,7 +14,7 @@ from ._lib import (EPI_ACCUM, EPI_BIAS, EPI_COLSUM, EPI_DGELU, EPI_DROPOUT, EPI_
 
 def gemm(a, b, *, a_major=0, b_major=0, bias=None, residual=None, aux=None, out=None,
          gelu=False, dgelu=False, accumulate=False, out_fp32=False, colsum=None,
-         dropout_p=0.0, rng_seed=0, rng_stream=0, tile_n=0, max_ctas=0):
+         dropout_p=0.0, rng_seed=0, rng_stream=0, tile_n=0, max_ctas=0, cluster=0, _debug_flags=0):
     """D = epilogue(A . B^T) on the tcgen05 GEMM core.  Returns `out` (and pre-activation if gelu).
 
     a: [M,K] (a_major=0) or [K,M] (a_major=1);  b: [N,K] (b_major=0) or [K,N] (b_major=1).
@@ -51,6 +51,7 @@ def gemm(a, b, *, a_major=0, b_major=0, bias=None, residual=None, aux=None, out=
         epi |= EPI_OUT_F32
     if colsum is not None:
         epi |= EPI_COLSUM
+    epi |= _debug_flags
     args = _lib.GemmArgs(
         a=a.data_ptr(), b=b.data_ptr(), lda=a.stride(0), ldb=b.stride(0),
         a_major=a_major, b_major=b_major, M=M, N=N, K=K,
@@ -61,7 +62,7 @@ def gemm(a, b, *, a_major=0, b_major=0, bias=None, residual=None, aux=None, out=
         ldaux=aux.stride(0) if aux is not None else 0,
         ldo=out.stride(0),
         dropout_p=float(dropout_p), rng_seed=int(rng_seed), rng_stream=int(rng_stream),
-        tile_n=int(tile_n), max_ctas=int(max_ctas))
+        tile_n=int(tile_n), max_ctas=int(max_ctas), cluster=int(cluster))
     _lib.check(lib.ub200_gemm(C.byref(args), _lib.current_stream()))
     return (out, out2) if gelu else out
 
