@@ -167,6 +167,10 @@ typedef struct {
   int32_t rows, hidden, dtype;
   float dropout_p;
   uint64_t rng_seed, rng_stream;
+  const int32_t* row_kind;  /* optional [rows]: only rows with row_kind[r] == kind are processed
+                               (the embedding front-end has different LayerNorms per row kind) */
+  int32_t kind;
+  int32_t dropout_on_dy;    /* 1: y = dropout(LN(x)) (embeddings): mask dy instead of emitting dx_drop */
 } ub200_ln_bwd_args;
 int ub200_layernorm_bwd(const ub200_ln_bwd_args* args, ub200_stream_t stream);
 
@@ -239,6 +243,52 @@ int ub200_encoder_bwd(const ub200_encoder_desc* d, const ub200_layer_weights* la
                       void* const* layer_out, const void* act, const void* const* d_layer_out,
                       void* dx_in, void* scratch, int32_t accumulate_wgrad,
                       ub200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Embedding front-end, computed straight into packed rows (model/model.py:217-334).
+ *
+ * ub200_embed_prep: per packed row t (= position pack_idx[t] = b*L + j of the attention mask)
+ *   src = gather_index[b, j] (joint mode) or j; text row iff src < Lt.  Emits int32 arrays
+ *   kind (0 text / 1 image), word_id, pos_id, type_id, img_src (= b*Li + region or -1),
+ *   mask_flag (img_masks).  Pure integer logic: bit-exact by construction.
+ * ub200_embed_gather_cast: out[t] = 16-bit(img_feat[img_src[t]] (+ mask_row if mask_flag[t])),
+ *   zeros for text rows  ->  A operand [T, D] of the img_linear GEMM (ub200_gemm, bias epilogue).
+ * ub200_embed_rows_fwd: text  x = dropout(LN_txt(word + pos + type))             (:232-245)
+ *                       image x = dropout(LN_out(LN_img(G) + LN_pos(box W^T + b) + type)) (:261-272)
+ *   u (pre-final-LN sum) and ppre (pos_linear output) are saved for the backward, which is
+ *   ub200_layernorm_bwd with row_kind masks + wgrad GEMMs + table scatter.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const int32_t* pack_idx;     /* [T] */
+  const int64_t* gather_index; /* [B, L] (joint) */
+  const int64_t* input_ids;    /* [B, Lt] */
+  const int64_t* position_ids; /* [pos_rows, Lt], pos_rows = 1 (broadcast) or B */
+  const int64_t* txt_type_ids; /* [B, Lt] or NULL (0) */
+  const int64_t* img_type_ids; /* [B, Li] or NULL (1) */
+  const uint8_t* img_masks;    /* [B, Li] bool/uint8 or NULL */
+  int32_t T, L, Lt, Li, pos_rows, mode;   /* mode: 0 joint, 1 text only, 2 image only */
+  int32_t *kind, *word_id, *pos_id, *type_id, *img_src, *mask_flag;   /* outputs, [T] each */
+} ub200_embed_prep_args;
+int ub200_embed_prep(const ub200_embed_prep_args* args, ub200_stream_t stream);
+
+int ub200_embed_gather_cast(const void* img_feat, int32_t feat_is_f32, const int32_t* img_src,
+                            const int32_t* mask_flag, const void* mask_row, void* out, int32_t T,
+                            int32_t D, int32_t dtype, ub200_stream_t stream);
+
+typedef struct {
+  const int32_t *kind, *word_id, *pos_id, *type_id, *img_src;          /* from ub200_embed_prep */
+  const void *word_emb, *pos_emb, *type_emb;                           /* embedding tables, 16-bit */
+  const void *ln_txt_g, *ln_txt_b;                                     /* embeddings.LayerNorm */
+  const void* img_linear_out;                                          /* [T, H] 16-bit */
+  const float* pos_feat;                                               /* [B*Li, 7] fp32 */
+  const void *w_pos, *b_pos;                                           /* pos_linear [H,7], [H] */
+  const void *ln_img_g, *ln_img_b, *ln_pos_g, *ln_pos_b, *ln_out_g, *ln_out_b;
+  void *x, *u, *ppre;                                                  /* [T, H] 16-bit outputs */
+  int32_t T, hidden, dtype;
+  float dropout_p;
+  uint64_t rng_seed, rng_stream;
+} ub200_embed_rows_args;
+int ub200_embed_rows_fwd(const ub200_embed_rows_args* args, ub200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -227,3 +227,131 @@ def test_no_fp32_or_cpu_fallback():
     with pytest.raises(RuntimeError):
         m(b["input_ids"], b["position_ids"], b["img_feat"], b["img_pos_feat"], b["attn_masks"],
           b["gather_index"])
+
+
+def _front(model, b, gi, training=False):
+    """Packed embedding rows through the fused front-end (internal entry used by forward())."""
+    from uniter_b200.model import _EmbedFront
+    meta = model._pack_meta(b["attn_masks"])
+    te, ie = model.embeddings, model.img_embeddings
+    model._weight_table()
+    x = _EmbedFront.apply(
+        model, meta, 0, b["input_ids"], b["position_ids"], b["img_feat"], b["img_pos_feat"], gi,
+        None, None, None, 0.0,
+        te.word_embeddings.weight, te.position_embeddings.weight, te.token_type_embeddings.weight,
+        te.LayerNorm.weight, te.LayerNorm.bias, ie.img_linear.weight, ie.img_linear.bias,
+        ie.img_layer_norm.weight, ie.img_layer_norm.bias, ie.pos_layer_norm.weight,
+        ie.pos_layer_norm.bias, ie.pos_linear.weight, ie.pos_linear.bias,
+        ie.mask_embedding.weight, ie.LayerNorm.weight, ie.LayerNorm.bias)
+    return x, meta
+
+
+@pytest.mark.parametrize("name", ["tiny_adv_perm", "tiny_adv_malformed"])
+def test_fused_front_end_honours_gather_index_bit_exactly(name):
+    """Forward path (ub200_embed_prep + gather_cast + GEMM + rows kernel): a packed row's value
+    depends only on its SOURCE row, so with an arbitrary gather_index every output row must equal,
+    bit for bit, the row the canonical index produces for the same source; and it matches the
+    reference's embedding output within fp16 rounding."""
+    g = util.load_golden(name)
+    cfg, batch = util.TINY, util.tiny_batch()
+    model = util.make_model(cfg, util.make_state(cfg), torch.float16).eval()
+    b = util.batch_to(batch, "cuda")
+    gi_adv = torch.from_numpy(g["gather_index"]).cuda()
+    with torch.no_grad():
+        x_adv, meta = _front(model, b, gi_adv)
+        x_can, _ = _front(model, b, b["gather_index"])
+    B, L = b["attn_masks"].shape
+    pad = lambda x: torch.zeros(B * L, x.size(1), device="cuda", dtype=x.dtype).index_copy_(
+        0, meta["pack_idx"].long(), x).view(B, L, -1)
+    xa, xc = pad(x_adv), pad(x_can)
+    Lt = b["input_ids"].size(1)
+    checked = 0
+    for bi in range(B):
+        n = int(b["attn_masks"][bi].sum())
+        can = {int(b["gather_index"][bi, j]): j for j in range(n)}
+        for j in range(n):
+            src = int(gi_adv[bi, j])
+            if src in can:
+                assert torch.equal(xa[bi, j], xc[bi, can[src]]), (bi, j, src)
+                checked += 1
+    assert checked > 20
+    v = b["attn_masks"].bool().cpu()
+    err = (xa.float().cpu() - torch.from_numpy(g["embedding_output"]))[v].abs().max().item()
+    assert err <= 1e-2, err
+
+
+def test_embed_prep_integer_logic_is_exact():
+    import ctypes as C
+    from uniter_b200 import _lib
+    from uniter_b200.model import _bind
+    lib = _bind()
+    torch.manual_seed(0)
+    B, Lt, Li = 5, 9, 7
+    L = Lt + Li
+    am = (torch.rand(B, L) < 0.7).long().cuda()
+    am[:, 0] = 1
+    pack = am.reshape(-1).nonzero().squeeze(1).to(torch.int32)
+    T = pack.numel()
+    gi = torch.randint(0, Lt + Li, (B, L)).cuda()
+    ids = torch.randint(0, 1000, (B, Lt)).cuda()
+    pos = torch.randint(0, 64, (B, Lt)).cuda()
+    tt = torch.randint(0, 2, (B, Lt)).cuda()
+    it = torch.randint(0, 3, (B, Li)).cuda()
+    msk = (torch.rand(B, Li) < 0.3).to(torch.uint8).cuda()
+    out = torch.empty(6, T, device="cuda", dtype=torch.int32)
+    a = _lib.EmbedPrepArgs(pack_idx=pack.data_ptr(), gather_index=gi.data_ptr(), input_ids=ids.data_ptr(),
+                           position_ids=pos.data_ptr(), txt_type_ids=tt.data_ptr(), img_type_ids=it.data_ptr(),
+                           img_masks=msk.data_ptr(), T=T, L=L, Lt=Lt, Li=Li, pos_rows=B, mode=0,
+                           kind=out[0].data_ptr(), word_id=out[1].data_ptr(), pos_id=out[2].data_ptr(),
+                           type_id=out[3].data_ptr(), img_src=out[4].data_ptr(), mask_flag=out[5].data_ptr())
+    _lib.check(lib.ub200_embed_prep(C.byref(a), _lib.current_stream()))
+    torch.cuda.synchronize()
+    bb = (pack.long() // L)
+    src = gi.reshape(-1)[pack.long()]
+    is_txt = src < Lt
+    st = src.clamp(max=Lt - 1)
+    si = (src - Lt).clamp(min=0)
+    assert torch.equal(out[0].long(), (~is_txt).long())
+    assert torch.equal(out[1].long()[is_txt], ids[bb, st][is_txt])
+    assert torch.equal(out[2].long()[is_txt], pos[bb, st][is_txt])
+    assert torch.equal(out[3].long(), torch.where(is_txt, tt[bb, st], it[bb, si]))
+    assert torch.equal(out[4].long()[~is_txt], (bb * Li + si)[~is_txt])
+    assert (out[4][is_txt] == -1).all()
+    assert torch.equal(out[5].long()[~is_txt], msk[bb, si].long()[~is_txt])
+
+
+def test_img_masks_and_type_ids_match_oracle():
+    """MRM-style forward: img_masks add mask_embedding[1]; custom type ids; gradients reach
+    mask_embedding and the 3-row type table (model/model.py:262-265, model/nlvr2.py:26-34)."""
+    cfg, dtype = util.TINY, torch.float16
+    state = util.make_state(cfg)
+    model = util.make_model(cfg, state, dtype).eval()
+    batch = util.tiny_batch()
+    b = util.batch_to(batch, "cuda")
+    g = torch.Generator().manual_seed(3)
+    img_masks = torch.rand(b["img_feat"].shape[:2], generator=g) < 0.3
+    out = model(b["input_ids"], b["position_ids"], b["img_feat"], b["img_pos_feat"], b["attn_masks"],
+                b["gather_index"], img_masks=img_masks.cuda(), output_all_encoded_layers=False)
+    rs = {k: v.half().float().requires_grad_(True) for k, v in state.items()}
+    ref = orc.uniter_forward(rs, 2, 2, batch["input_ids"], batch["position_ids"],
+                             batch["img_feat"].half().float(), batch["img_pos_feat"].half().float(),
+                             batch["attn_masks"], batch["gather_index"], img_masks=img_masks,
+                             output_all_encoded_layers=False)
+    v = batch["attn_masks"].bool()
+    assert (out.float().cpu() - ref.detach())[v].abs().max().item() <= 1e-2
+    m = b["attn_masks"].float()
+    (((out.float() * m[..., None]) ** 2).sum() / m.sum() * 64).backward()
+    mc = batch["attn_masks"].float()
+    (((ref * mc[..., None]) ** 2).sum() / mc.sum() * 64).backward()
+    gm = model.img_embeddings.mask_embedding.weight.grad.float().cpu()
+    gr = rs["img_embeddings.mask_embedding.weight"].grad
+    assert ((gm[1] - gr[1]).norm() / gr[1].norm()).item() < 5e-2
+    for name in ("embeddings.word_embeddings.weight", "embeddings.position_embeddings.weight",
+                 "embeddings.token_type_embeddings.weight", "img_embeddings.pos_linear.weight",
+                 "img_embeddings.img_linear.weight", "img_embeddings.img_layer_norm.weight",
+                 "img_embeddings.pos_layer_norm.bias", "img_embeddings.LayerNorm.weight",
+                 "embeddings.LayerNorm.bias", "img_embeddings.pos_linear.bias", "img_embeddings.img_linear.bias"):
+        got = dict(model.named_parameters())[name].grad.float().cpu()
+        want = rs[name].grad
+        rel = ((got - want).norm() / (want.norm() + 1e-9)).item()
+        assert rel < 5e-2, (name, rel)

@@ -46,7 +46,29 @@ class LnBwdArgs(C.Structure):
         ("dx_drop", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("dbias", C.c_void_p),
         ("rows", C.c_int32), ("hidden", C.c_int32), ("dtype", C.c_int32),
         ("dropout_p", C.c_float), ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64),
+        ("row_kind", C.c_void_p), ("kind", C.c_int32), ("dropout_on_dy", C.c_int32),
     ]
+
+
+class EmbedPrepArgs(C.Structure):
+    _fields_ = [
+        ("pack_idx", C.c_void_p), ("gather_index", C.c_void_p), ("input_ids", C.c_void_p),
+        ("position_ids", C.c_void_p), ("txt_type_ids", C.c_void_p), ("img_type_ids", C.c_void_p),
+        ("img_masks", C.c_void_p),
+        ("T", C.c_int32), ("L", C.c_int32), ("Lt", C.c_int32), ("Li", C.c_int32),
+        ("pos_rows", C.c_int32), ("mode", C.c_int32),
+        ("kind", C.c_void_p), ("word_id", C.c_void_p), ("pos_id", C.c_void_p),
+        ("type_id", C.c_void_p), ("img_src", C.c_void_p), ("mask_flag", C.c_void_p),
+    ]
+
+
+class EmbedRowsArgs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "kind", "word_id", "pos_id", "type_id", "img_src", "word_emb", "pos_emb", "type_emb",
+        "ln_txt_g", "ln_txt_b", "img_linear_out", "pos_feat", "w_pos", "b_pos",
+        "ln_img_g", "ln_img_b", "ln_pos_g", "ln_pos_b", "ln_out_g", "ln_out_b", "x", "u", "ppre")] + [
+        ("T", C.c_int32), ("hidden", C.c_int32), ("dtype", C.c_int32),
+        ("dropout_p", C.c_float), ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64)]
 
 
 _lib = None
@@ -80,6 +102,13 @@ def load():
     lib.ub200_colsum.restype = C.c_int
     lib.ub200_colsum.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32,
                                  C.c_void_p]
+    lib.ub200_embed_prep.restype = C.c_int
+    lib.ub200_embed_prep.argtypes = [C.POINTER(EmbedPrepArgs), C.c_void_p]
+    lib.ub200_embed_gather_cast.restype = C.c_int
+    lib.ub200_embed_gather_cast.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.ub200_embed_rows_fwd.restype = C.c_int
+    lib.ub200_embed_rows_fwd.argtypes = [C.POINTER(EmbedRowsArgs), C.c_void_p]
     _lib = lib
     return lib
 

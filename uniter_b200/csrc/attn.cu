@@ -104,7 +104,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   const float c = p.scale * 1.4426950408889634f;  // scale * log2(e)
   uint32_t ph_load = 0, ph_mma = 0;
 
-  // ---------------------------------------------------------------- sweep 1: row max / sum
+  // ---------------------------------------------------------------- sweep 1: row max
   float m = -INFINITY, l = 0.f;
   for (int j = 0; j < nkv; ++j) {
     const int kv_len = min(ATT_BN, S - j * ATT_BN);
@@ -128,36 +128,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1;
     tc_fence_after();
-    // pass A: block max
-    float bm = -INFINITY;
     for (int cc = 0; cc * 32 < kv_len; ++cc) {
       uint32_t r[32];
       tmem_ld32(tS + lane_off + cc * 32, r);
       tmem_ld_wait();
+      if ((cc + 1) * 32 <= kv_len) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (cc * 32 + i < kv_len) bm = fmaxf(bm, __uint_as_float(r[i]));
-    }
-    const float m_new = fmaxf(m, bm);
-    float bl = 0.f;
-    for (int cc = 0; cc * 32 < kv_len; ++cc) {
-      uint32_t r[32];
-      tmem_ld32(tS + lane_off + cc * 32, r);
-      tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
+      } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (cc * 32 + i < kv_len) bl += exp2f((__uint_as_float(r[i]) - m_new) * c);
+        for (int i = 0; i < 32; ++i)
+          if (cc * 32 + i < kv_len) m = fmaxf(m, __uint_as_float(r[i]));
+      }
     }
-    l = l * exp2f((m - m_new) * c) + bl;
-    m = m_new;
     if (nkv > 1) {  // S (TMEM) and sK are about to be overwritten
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
     }
   }
-  const float inv_l = 1.f / l;
-  if (q_ok) p.lse[static_cast<size_t>(head) * p.T + seq0 + qrow] = m * p.scale + logf(l);
+  const float mc = m * c;
 
   // ---------------------------------------------------------------- sweep 2: P and O = P V
   for (int j = 0; j < nkv; ++j) {
@@ -195,7 +185,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float s = __uint_as_float(r[g * 8 + i]);
-          pv[i] = (key0 + i < kv_len) ? exp2f((s - m) * c) * inv_l : 0.f;
+          // unnormalised probability exp(scale*(s - max)) in (0, 1]; O is divided by the row sum
+          // at the end (the 1/l factor commutes with dropout and with P.V)
+          pv[i] = (key0 + i < kv_len) ? ex2_approx(fmaf(s, c, -mc)) : 0.f;
+          l += pv[i];
         }
         if (p.drop_thr16) {
           DropoutRng rng;
@@ -236,7 +229,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     tc_fence_after();
   }
 
-  // ---------------------------------------------------------------- epilogue: O -> ctx[T, H]
+  // ---------------------------------------------------------------- epilogue: O / l -> ctx[T, H]
+  const float inv_l = 1.f / l;
+  if (q_ok) p.lse[static_cast<size_t>(head) * p.T + seq0 + qrow] = m * p.scale + logf(l);
   {
     typename Elem<kBF16>::T* out = reinterpret_cast<typename Elem<kBF16>::T*>(p.ctx) +
                                    static_cast<size_t>(seq0 + qrow) * p.H + head * ATT_D;
@@ -249,10 +244,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 u;
-          u.x = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1]));
-          u.y = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3]));
-          u.z = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]));
-          u.w = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7]));
+          u.x = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 0]) * inv_l, __uint_as_float(r[g * 8 + 1]) * inv_l);
+          u.y = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 2]) * inv_l, __uint_as_float(r[g * 8 + 3]) * inv_l);
+          u.z = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 4]) * inv_l, __uint_as_float(r[g * 8 + 5]) * inv_l);
+          u.w = Elem<kBF16>::pack(__uint_as_float(r[g * 8 + 6]) * inv_l, __uint_as_float(r[g * 8 + 7]) * inv_l);
           *reinterpret_cast<uint4*>(out + cc * 32 + g * 8) = u;
         }
       }
@@ -277,7 +272,7 @@ constexpr int ATT_FWD_SMEM = 5 * ATT_TILE + 64 + 1024;
 // dQ of a sequence longer than one key block is accumulated with fp32 atomics in `dq_accum`.
 // =====================================================================================
 template <bool kBF16>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const AttnParams p, float* dq_accum) {
   using T16 = typename Elem<kBF16>::T;
@@ -303,7 +298,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* bar_mma = bar_load + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
 
+  // 256 threads: thread pair (row, chalf) — both own TMEM lane `row`, each handles half of the
+  // 32-column blocks (twice the warps per SM and half the serial softmax work per thread)
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row_t = tid & 127;
+  const int chalf = tid >> 7;
   if (tid == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
@@ -320,7 +319,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
-  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const int bh = b * p.nheads + head;
   const float c = p.scale * 1.4426950408889634f;
   const uint32_t fmt = kBF16 ? 1 : 0;
@@ -329,7 +328,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   for (int i = 0; i < nq; ++i) {
     const int q_len = min(ATT_BM, S - i * ATT_BM);
     const int q_pad = (q_len + 15) & ~15;
-    const int qrow = i * ATT_BM + tid;
+    const int qrow = i * ATT_BM + row_t;
     const bool q_ok = qrow < S;
     if (tid == 0) {
       mbar_expect_tx(bar_load, (i == 0 ? 4 : 2) * ATT_TILE);
@@ -376,7 +375,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     ph_mma ^= 1;
     tc_fence_after();
 
-    for (int cc = 0; cc * 32 < n_pad; ++cc) {
+    for (int cc = chalf * 2; cc < chalf * 2 + 2 && cc * 32 < n_pad; ++cc) {
       uint32_t rs[32], rp[32];
       tmem_ld32(tS + lane_off + cc * 32, rs);
       tmem_ld32(tP + lane_off + cc * 32, rp);
@@ -395,7 +394,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const bool ok = q_ok && (key0 + e < kv_len);
-          float pr = ok ? exp2f(__uint_as_float(rs[g * 8 + e]) * c - lse2) : 0.f;
+          float pr = ok ? ex2_approx(fmaf(__uint_as_float(rs[g * 8 + e]), c, -lse2)) : 0.f;
           pr = Elem<kBF16>::to_f(Elem<kBF16>::from_f(pr));   // P as the forward rounded it
           float dp = __uint_as_float(rp[g * 8 + e]);
           float pdv = pr;
@@ -410,10 +409,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         uint4 u;
         u.x = Elem<kBF16>::pack(pd[0], pd[1]); u.y = Elem<kBF16>::pack(pd[2], pd[3]);
         u.z = Elem<kBF16>::pack(pd[4], pd[5]); u.w = Elem<kBF16>::pack(pd[6], pd[7]);
-        st_swz128(sP, tid, key0, u);
+        st_swz128(sP, row_t, key0, u);
         u.x = Elem<kBF16>::pack(ds[0], ds[1]); u.y = Elem<kBF16>::pack(ds[2], ds[3]);
         u.z = Elem<kBF16>::pack(ds[4], ds[5]); u.w = Elem<kBF16>::pack(ds[6], ds[7]);
-        st_swz128(sDS, tid, key0, u);
+        st_swz128(sDS, row_t, key0, u);
       }
     }
     fence_proxy_async_smem();
@@ -445,9 +444,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1;
     tc_fence_after();
-    // dQ_i out (rows = queries)
-#pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
+    // dQ_i out (rows = queries); each thread of the pair writes one 32-column half
+    {
+      const int cc = chalf;
       uint32_t r[32];
       tmem_ld32(tdQ + lane_off + cc * 32, r);
       tmem_ld_wait();
@@ -480,15 +479,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   // dK_j, dV_j out (rows = keys)
   {
-    const int key = j * ATT_BN + tid;
+    const int key = j * ATT_BN + row_t;
     const bool k_ok = key < S;
     T16* outk = reinterpret_cast<T16*>(p.dqkv) + static_cast<size_t>(seq0 + key) * (3 * p.H) +
                 p.H + head * ATT_D;
     T16* outv = outk + p.H;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
+      {
+        const int cc = chalf;
         uint32_t r[32];
         tmem_ld32((which ? tdV : tdK) + lane_off + cc * 32, r);
         tmem_ld_wait();
@@ -659,8 +658,8 @@ extern "C" int ub200_attn_bwd(const ub200_attn_args* args, ub200_stream_t stream
   }
   {
     ProfScope ps(stream);
-    if (di) attn_bwd_kernel<true><<<grid, 128, ATT_BWD_SMEM, stream>>>(tmQ, tmD, p, acc);
-    else attn_bwd_kernel<false><<<grid, 128, ATT_BWD_SMEM, stream>>>(tmQ, tmD, p, acc);
+    if (di) attn_bwd_kernel<true><<<grid, 256, ATT_BWD_SMEM, stream>>>(tmQ, tmD, p, acc);
+    else attn_bwd_kernel<false><<<grid, 256, ATT_BWD_SMEM, stream>>>(tmQ, tmD, p, acc);
   }
   UB_CHECK_CUDA(cudaGetLastError());
   if (multi) {

@@ -313,6 +313,12 @@ __device__ __forceinline__ uint32_t rand16_of(const uint4& r, int lane8) {
   return (lane8 & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Standard-normal CDF Phi(x) through erf(|x|/sqrt2) = 1 - poly(t) * exp(-x^2/2),
 // t = 1/(1 + p|x|/sqrt2)  (Abramowitz & Stegun 7.1.26, |abs err| <= 1.5e-7 — far below the
 // 16-bit output rounding).  `ex` returns exp(-x^2/2), shared with the pdf in the derivative.

@@ -101,6 +101,9 @@ struct LnBwdParams {
   uint32_t drop_thr16;
   float drop_inv_keep;
   uint32_t seed_lo, seed_hi, stream_lo, stream_hi;
+  const int* row_kind;  // optional [rows]: only rows with row_kind[row] == kind take part
+  int kind;
+  int dy_drop;          // 1: the dropout mask applies to dy (y = dropout(LN(x)), embeddings)
 };
 
 // NV = vectors (8 columns) per lane = ceil(H / 256): register arrays are sized for the actual
@@ -155,6 +158,20 @@ ln_bwd_kernel(const LnBwdParams p) {
         for (int e = 0; e < 8; ++e) sum += xv[i][e];
       }
     }
+    if (p.dy_drop) {                 // y = dropout(LN(x)): mask the incoming gradient
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) {
+          const uint64_t el = static_cast<uint64_t>(row) * H + vi * 8;
+          const uint4 rnd = rng.draw8(el >> 3);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            dv[i][e] = (rand16_of(rnd, e) < rng.thr16) ? 0.f : dv[i][e] * rng.inv_keep;
+        }
+      }
+    }
+    const bool active = (p.row_kind == nullptr) || (p.row_kind[row] == p.kind);
     const int nrow = row + stride;   // prefetch the next row of this warp
     if (nrow < p.rows) {
 #pragma unroll
@@ -168,6 +185,7 @@ ln_bwd_kernel(const LnBwdParams p) {
         }
       }
     }
+    if (!active) continue;           // row belongs to the other LayerNorm (embedding front-end)
     const float mean = warp_sum(sum) * inv_h;
     float sq = 0.f;
 #pragma unroll
@@ -206,7 +224,7 @@ ln_bwd_kernel(const LnBwdParams p) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = rstd * (dv[i][e] - s1 - xv[i][e] * s2);
         dxr[vi] = pack8<kBF16>(o);
-        if (ddr) {
+        if (ddr && !p.dy_drop) {
           const uint64_t el = static_cast<uint64_t>(row) * H + vi * 8;
           const uint4 rnd = rng.draw8(el >> 3);
 #pragma unroll
@@ -450,11 +468,14 @@ extern "C" int ub200_layernorm_bwd(const ub200_ln_bwd_args* a, ub200_stream_t st
   p.dy = a->dy; p.x = a->x; p.gamma = a->gamma; p.dx = a->dx;
   p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.dbias = a->dbias;
   p.rows = a->rows; p.H = a->hidden;
+  p.row_kind = a->row_kind; p.kind = a->kind; p.dy_drop = 0;
   if (a->dropout_p > 0.f) {
-    UB_CHECK_ARG(a->dx_drop, "layernorm_bwd: dropout_p > 0 needs dx_drop");
+    UB_CHECK_ARG(a->dx_drop || a->dropout_on_dy, "layernorm_bwd: dropout_p > 0 needs dx_drop");
     uint32_t thr = static_cast<uint32_t>(a->dropout_p * 65536.0f + 0.5f);
     if (thr > 65535u) thr = 65535u;
-    p.dx_drop = a->dx_drop;
+    if (thr == 0u) thr = 1u;
+    p.dx_drop = a->dropout_on_dy ? nullptr : a->dx_drop;
+    p.dy_drop = a->dropout_on_dy ? 1 : 0;
     p.drop_thr16 = thr;
     p.drop_inv_keep = 65536.0f / static_cast<float>(65536u - thr);
   } else {

@@ -372,6 +372,130 @@ class _GatherRows(torch.autograd.Function):
         return out.view(ctx.src_shape), None, None, None
 
 
+class _EmbedFront(torch.autograd.Function):
+    """Embedding front-end straight into packed rows (model/model.py:217-334) on libub200:
+    ub200_embed_prep -> ub200_embed_gather_cast -> ub200_gemm (img_linear) -> ub200_embed_rows_fwd.
+    Backward: row-kind masked ub200_layernorm_bwd x4, wgrad GEMM for img_linear, table scatter."""
+
+    @staticmethod
+    def forward(ctx, model, meta, mode, input_ids, position_ids, img_feat, img_pos_feat, gather_index,
+                img_masks, txt_type_ids, img_type_ids, dropout_p,
+                word_w, pos_w, type_w, lnt_g, lnt_b, img_w, img_b, lni_g, lni_b, lnp_g, lnp_b,
+                posl_w, posl_b, mask_w, lnf_g, lnf_b):
+        from . import ops
+        lib = _bind()
+        T, L = meta["total"], meta["L"]
+        dev, dtype = word_w.device, word_w.dtype
+        H = word_w.size(1)
+        dt = _lib.dtype_code(dtype)
+        stream = _lib.current_stream()
+        idx = torch.empty(6, T, device=dev, dtype=torch.int32)
+        Lt = input_ids.size(1) if input_ids is not None else 0
+        Li = img_feat.size(1) if img_feat is not None else 0
+        if input_ids is not None:
+            input_ids = input_ids.contiguous()
+            position_ids = position_ids.contiguous()
+        if img_masks is not None:
+            img_masks = img_masks.to(torch.uint8).contiguous()
+        a = _lib.EmbedPrepArgs(
+            pack_idx=meta["pack_idx"].data_ptr(),
+            gather_index=gather_index.contiguous().data_ptr() if mode == 0 else None,
+            input_ids=_lib.ptr(input_ids), position_ids=_lib.ptr(position_ids),
+            txt_type_ids=_lib.ptr(txt_type_ids.contiguous() if txt_type_ids is not None else None),
+            img_type_ids=_lib.ptr(img_type_ids.contiguous() if img_type_ids is not None else None),
+            img_masks=_lib.ptr(img_masks), T=T, L=L, Lt=Lt, Li=Li,
+            pos_rows=position_ids.size(0) if position_ids is not None else 1, mode=mode,
+            kind=idx[0].data_ptr(), word_id=idx[1].data_ptr(), pos_id=idx[2].data_ptr(),
+            type_id=idx[3].data_ptr(), img_src=idx[4].data_ptr(), mask_flag=idx[5].data_ptr())
+        _lib.check(lib.ub200_embed_prep(C.byref(a), stream))
+        A = G = pos_feat = None
+        if mode != 1:
+            if img_feat.dtype not in (torch.float32, dtype):
+                img_feat = img_feat.to(dtype)
+            img_feat = img_feat.contiguous()
+            D = img_feat.size(-1)
+            A = torch.empty(T, D, device=dev, dtype=dtype)
+            mask_row = mask_w[1].contiguous()
+            _lib.check(lib.ub200_embed_gather_cast(
+                img_feat.data_ptr(), 1 if img_feat.dtype == torch.float32 else 0, idx[4].data_ptr(),
+                idx[5].data_ptr(), mask_row.data_ptr(), A.data_ptr(), T, D, dt, stream))
+            G = ops.gemm(A, img_w, bias=img_b)                       # img_linear on the tcgen05 core
+            pos_feat = img_pos_feat.float().contiguous().view(-1, img_pos_feat.size(-1))
+            assert pos_feat.size(1) == 7
+        x = torch.empty(T, H, device=dev, dtype=dtype)
+        u = torch.empty_like(x)
+        ppre = torch.empty_like(x)
+        _rng_offset[0] += 1
+        seed = torch.cuda.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        rng_stream = (_rng_offset[0] << 20) | (0xFFFF << 4) | 4
+        r = _lib.EmbedRowsArgs(
+            kind=idx[0].data_ptr(), word_id=idx[1].data_ptr(), pos_id=idx[2].data_ptr(),
+            type_id=idx[3].data_ptr(), img_src=idx[4].data_ptr(),
+            word_emb=word_w.data_ptr(), pos_emb=pos_w.data_ptr(), type_emb=type_w.data_ptr(),
+            ln_txt_g=lnt_g.data_ptr(), ln_txt_b=lnt_b.data_ptr(),
+            img_linear_out=_lib.ptr(G), pos_feat=_lib.ptr(pos_feat),
+            w_pos=posl_w.contiguous().data_ptr(), b_pos=posl_b.data_ptr(),
+            ln_img_g=lni_g.data_ptr(), ln_img_b=lni_b.data_ptr(), ln_pos_g=lnp_g.data_ptr(),
+            ln_pos_b=lnp_b.data_ptr(), ln_out_g=lnf_g.data_ptr(), ln_out_b=lnf_b.data_ptr(),
+            x=x.data_ptr(), u=u.data_ptr(), ppre=ppre.data_ptr(), T=T, hidden=H, dtype=dt,
+            dropout_p=float(dropout_p), rng_seed=seed, rng_stream=rng_stream)
+        _lib.check(lib.ub200_embed_rows_fwd(C.byref(r), stream))
+        ctx.mode, ctx.dropout_p, ctx.seed, ctx.rng_stream = mode, float(dropout_p), seed, rng_stream
+        ctx.has_masks = img_masks is not None
+        ctx.shapes = (word_w.shape, pos_w.shape, type_w.shape, posl_w.shape, mask_w.shape)
+        ctx.save_for_backward(idx, A, G, u, ppre, pos_feat, lnt_g, lni_g, lnp_g, lnf_g, img_w)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        from . import ops
+        idx, A, G, u, ppre, pos_feat, lnt_g, lni_g, lnp_g, lnf_g, img_w = ctx.saved_tensors
+        dx = dx.contiguous()
+        T, H = dx.shape
+        dtype, dev = dx.dtype, dx.device
+        kind, word_id, pos_id, type_id, img_src, mask_flag = (idx[i] for i in range(6))
+        kw = dict(dropout_p=ctx.dropout_p, rng_seed=ctx.seed, rng_stream=ctx.rng_stream,
+                  row_kind=kind, dropout_on_dy=ctx.dropout_p > 0)
+        word_shape, pos_shape, type_shape, posl_shape, mask_shape = ctx.shapes
+        du = torch.zeros_like(dx)
+        g = {}
+        if ctx.mode != 2:
+            _, _, g["lnt_g"], g["lnt_b"], _ = ops.layernorm_bwd(dx, u, lnt_g, kind=0, dx=du,
+                                                                want_dbias=False, **kw)
+        if ctx.mode != 1:
+            _, _, g["lnf_g"], g["lnf_b"], _ = ops.layernorm_bwd(dx, u, lnf_g, kind=1, dx=du,
+                                                                want_dbias=False, **kw)
+        d_type = torch.zeros(type_shape, device=dev, dtype=torch.float32)
+        d_type.index_add_(0, type_id.long(), du.float())
+        d_word = d_pos = None
+        if ctx.mode != 2:
+            du_txt = du * (kind == 0).unsqueeze(1)
+            d_word = torch.zeros(word_shape, device=dev, dtype=dtype)
+            d_word.index_add_(0, word_id.long(), du_txt)
+            d_pos = torch.zeros(pos_shape, device=dev, dtype=torch.float32)
+            d_pos.index_add_(0, pos_id.long(), du_txt.float())
+        d_img_w = d_img_b = d_posl_w = d_posl_b = d_mask = None
+        if ctx.mode != 1:
+            dG, _, g["lni_g"], g["lni_b"], d_img_b = ops.layernorm_bwd(du, G, lni_g, row_kind=kind, kind=1)
+            dP, _, g["lnp_g"], g["lnp_b"], d_posl_b = ops.layernorm_bwd(du, ppre, lnp_g, row_kind=kind, kind=1)
+            # img_linear.weight [H, D] = dG^T A   (wgrad form: both operands read un-transposed)
+            d_img_w = ops.gemm(dG, A, a_major=1, b_major=1)
+            is_img = (kind == 1).unsqueeze(1)
+            F = (pos_feat[img_src.clamp(min=0).long()] * is_img).to(dtype)           # [T, 7]
+            d_posl_w = dP.t() @ F                                                   # [H, 7], K = T
+            if ctx.has_masks and ctx.needs_input_grad[25]:
+                dA = ops.gemm(dG, img_w, b_major=1)                                 # [T, D]
+                d_mask = torch.zeros(mask_shape, device=dev, dtype=dtype)
+                d_mask[1] = (dA.float() * (mask_flag != 0).unsqueeze(1)).sum(0).to(dtype)
+
+        def c(t):
+            return None if t is None else t.to(dtype)
+        return (None,) * 12 + (
+            d_word, c(d_pos), c(d_type), c(g.get("lnt_g")), c(g.get("lnt_b")),
+            d_img_w, c(d_img_b), c(g.get("lni_g")), c(g.get("lni_b")), c(g.get("lnp_g")), c(g.get("lnp_b")),
+            d_posl_w, c(d_posl_b), d_mask, c(g.get("lnf_g")), c(g.get("lnf_b")))
+
+
 class _EncoderStack(torch.autograd.Function):
     """NL x BertLayer over packed tokens: one C-ABI call forward, one backward."""
 
@@ -651,32 +775,32 @@ class UniterModel(UniterPreTrainedModel):
             raise ValueError("attention_mask selects no tokens")
         B, L = meta["batch"], meta["L"]
         H = self.config.hidden_size
-        if img_feat is not None:
-            img_feat = img_feat.to(dtype)
-            img_pos_feat = img_pos_feat.to(dtype)
-
-        # ---- embeddings (model/model.py:347-360), gathered straight into PACKED rows
+        # ---- embeddings (model/model.py:347-360) computed straight into PACKED rows by libub200
         if input_ids is None:
-            emb = self._compute_img_embeddings(img_feat, img_pos_feat, img_masks, img_type_ids)
-            src, src_idx, pack_inverse = emb.reshape(-1, H), meta["pack_idx"], meta["unpack_idx"]
-            if emb.size(1) != L:
-                raise ValueError("attention_mask length %d != number of regions %d" % (L, emb.size(1)))
+            mode = 2
+            if img_feat.size(1) != L:
+                raise ValueError("attention_mask length %d != number of regions %d" % (L, img_feat.size(1)))
         elif img_feat is None:
-            emb = self._compute_txt_embeddings(input_ids, position_ids, txt_type_ids)
-            src, src_idx, pack_inverse = emb.reshape(-1, H), meta["pack_idx"], meta["unpack_idx"]
-            if emb.size(1) != L:
-                raise ValueError("attention_mask length %d != text length %d" % (L, emb.size(1)))
+            mode = 1
+            if input_ids.size(1) != L:
+                raise ValueError("attention_mask length %d != text length %d" % (L, input_ids.size(1)))
         else:
-            txt_emb = self._compute_txt_embeddings(input_ids, position_ids, txt_type_ids)
-            img_emb = self._compute_img_embeddings(img_feat, img_pos_feat, img_masks, img_type_ids)
-            cat = torch.cat([txt_emb, img_emb], dim=1)
-            Lc = cat.size(1)
-            if gather_index.shape != (B, L):
+            mode = 0
+            if gather_index is None or gather_index.shape != (B, L):
                 raise ValueError("gather_index must be [B, L] like attention_mask")
-            flat_gi = (gather_index + torch.arange(B, device=cat.device).unsqueeze(1) * Lc).reshape(-1)
-            src, src_idx = cat.reshape(-1, H), flat_gi[meta["pack_idx"].long()].to(torch.int32)
-            pack_inverse = None  # arbitrary gather_index may repeat rows: scatter-add backward
-        x = _GatherRows.apply(src, src_idx.contiguous(), src.size(0), pack_inverse)  # [T, H] packed
+        te, ie = self.embeddings, self.img_embeddings
+        if self.training and te.dropout.p != ie.dropout.p:
+            raise NotImplementedError("text / image embedding dropout probabilities differ")
+        if img_masks is not None:
+            ie.mask_embedding.weight.data[0, :].fill_(0)          # model/model.py:263
+        x = _EmbedFront.apply(
+            self, meta, mode, input_ids, position_ids, img_feat, img_pos_feat, gather_index,
+            img_masks, txt_type_ids, img_type_ids, te.dropout.p if self.training else 0.0,
+            te.word_embeddings.weight, te.position_embeddings.weight, te.token_type_embeddings.weight,
+            te.LayerNorm.weight, te.LayerNorm.bias, ie.img_linear.weight, ie.img_linear.bias,
+            ie.img_layer_norm.weight, ie.img_layer_norm.bias, ie.pos_layer_norm.weight,
+            ie.pos_layer_norm.bias, ie.pos_linear.weight, ie.pos_linear.bias,
+            ie.mask_embedding.weight, ie.LayerNorm.weight, ie.LayerNorm.bias)       # [T, H] packed
 
         # ---- encoder stack on packed tokens
         if not hasattr(self, "_anchor") or self._anchor.device != x.device:

@@ -111,19 +111,25 @@ def layernorm_fwd(x, gamma, beta):
     return y
 
 
-def layernorm_bwd(dy, x, gamma, dropout_p=0.0, rng_seed=0, rng_stream=0, want_dbias=True):
+def layernorm_bwd(dy, x, gamma, dropout_p=0.0, rng_seed=0, rng_stream=0, want_dbias=True,
+                  row_kind=None, kind=0, dropout_on_dy=False, dx=None, dgamma=None, dbeta=None, dbias=None):
     """Returns dx, dx_drop (or None), dgamma, dbeta, dbias (fp32)."""
     lib = _lib.load()
     rows, H = x.shape
-    dx = torch.empty_like(x)
-    dx_drop = torch.empty_like(x) if dropout_p > 0 else None
-    dgamma = torch.zeros(H, device=x.device, dtype=torch.float32)
-    dbeta = torch.zeros_like(dgamma)
-    dbias = torch.zeros_like(dgamma) if want_dbias else None
+    if dx is None:
+        dx = torch.empty_like(x) if row_kind is None else torch.zeros_like(x)
+    dx_drop = torch.empty_like(x) if (dropout_p > 0 and not dropout_on_dy) else None
+    if dgamma is None:
+        dgamma = torch.zeros(H, device=x.device, dtype=torch.float32)
+    if dbeta is None:
+        dbeta = torch.zeros(H, device=x.device, dtype=torch.float32)
+    if dbias is None and want_dbias:
+        dbias = torch.zeros(H, device=x.device, dtype=torch.float32)
     a = _lib.LnBwdArgs(dy=dy.data_ptr(), x=x.data_ptr(), gamma=gamma.data_ptr(), dx=dx.data_ptr(),
                        dx_drop=_lib.ptr(dx_drop), dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(),
                        dbias=_lib.ptr(dbias), rows=rows, hidden=H, dtype=_lib.dtype_code(x.dtype),
-                       dropout_p=float(dropout_p), rng_seed=int(rng_seed), rng_stream=int(rng_stream))
+                       dropout_p=float(dropout_p), rng_seed=int(rng_seed), rng_stream=int(rng_stream),
+                       row_kind=_lib.ptr(row_kind), kind=int(kind), dropout_on_dy=1 if dropout_on_dy else 0)
     _lib.check(lib.ub200_layernorm_bwd(C.byref(a), _lib.current_stream()))
     return dx, dx_drop, dgamma, dbeta, dbias
 
