@@ -223,6 +223,8 @@ typedef struct {
   float hidden_dropout_p;        /* 0 when not training */
   float attn_dropout_p;
   uint64_t rng_seed, rng_offset; /* rng_offset must differ between forward calls */
+  int32_t layer_offset;          /* index of layers[0] in the whole stack (dropout streams are keyed
+                                    by the global layer index, so a backward may be issued in chunks) */
 } ub200_encoder_desc;
 
 /* bytes of saved activations per layer (fwd writes, bwd reads) and of backward scratch */

@@ -355,3 +355,25 @@ def test_img_masks_and_type_ids_match_oracle():
         want = rs[name].grad
         rel = ((got - want).norm() / (want.norm() + 1e-9)).item()
         assert rel < 5e-2, (name, rel)
+
+
+def test_chunked_backward_is_identical_to_single_call():
+    """The data-parallel reducer issues the backward in layer chunks; dropout streams are keyed by
+    the global layer index, so chunked and single-call backward must agree bit for bit (train mode,
+    dropout on, same forward)."""
+    cfg = util.TINY
+    model = util.make_model(cfg, util.make_state(cfg), torch.bfloat16).train()
+    out = _fwd(model, util.tiny_batch(), output_all_encoded_layers=False)
+    loss = out.float().pow(2).mean()
+    loss.backward(retain_graph=True)
+    g1 = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad(set_to_none=True)
+    calls = []
+    model._bwd_chunk_hook = lambda m, lo, hi: calls.append((lo, hi))
+    model._bwd_chunks = 2
+    loss.backward()
+    model._bwd_chunk_hook = None
+    assert calls == [(1, 2), (0, 1)]
+    for n, p in model.named_parameters():
+        if n in g1 and n.startswith("encoder."):
+            assert torch.equal(p.grad, g1[n]), n

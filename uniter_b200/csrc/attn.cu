@@ -62,6 +62,8 @@ __device__ __forceinline__ void st_swz128(uint8_t* base, int r, int col8, uint4 
 template <bool kBF16>
 __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();   // cu_seqlens / qkv come from preceding kernels
   const int b = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
   const int seq0 = p.cu_seqlens[b];
   const int S = p.cu_seqlens[b + 1] - seq0;
@@ -276,6 +278,8 @@ __global__ void __launch_bounds__(256)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const AttnParams p, float* dq_accum) {
   using T16 = typename Elem<kBF16>::T;
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.z, head = blockIdx.y, j = blockIdx.x;
   const int seq0 = p.cu_seqlens[b];
   const int S = p.cu_seqlens[b + 1] - seq0;
@@ -519,6 +523,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 template <bool kBF16>
 __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, void* dqkv,
                                        const int* __restrict__ cu_seqlens, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int seq0 = cu_seqlens[blockIdx.x];
   const int S = cu_seqlens[blockIdx.x + 1] - seq0;
   if (S <= ATT_BN) return;
@@ -585,7 +591,7 @@ extern "C" int ub200_attn_fwd(const ub200_attn_args* args, ub200_stream_t stream
       configured[1] = true;
     }
     ProfScope ps(stream);
-    attn_fwd_kernel<true><<<grid, 128, ATT_FWD_SMEM, stream>>>(tm, p);
+    UB_CHECK_CUDA(launch_pdl(attn_fwd_kernel<true>, grid, dim3(128), ATT_FWD_SMEM, stream, 1, tm, p));
   } else {
     if (!configured[0]) {
       UB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>,
@@ -593,7 +599,7 @@ extern "C" int ub200_attn_fwd(const ub200_attn_args* args, ub200_stream_t stream
       configured[0] = true;
     }
     ProfScope ps(stream);
-    attn_fwd_kernel<false><<<grid, 128, ATT_FWD_SMEM, stream>>>(tm, p);
+    UB_CHECK_CUDA(launch_pdl(attn_fwd_kernel<false>, grid, dim3(128), ATT_FWD_SMEM, stream, 1, tm, p));
   }
   UB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -658,14 +664,14 @@ extern "C" int ub200_attn_bwd(const ub200_attn_args* args, ub200_stream_t stream
   }
   {
     ProfScope ps(stream);
-    if (di) attn_bwd_kernel<true><<<grid, 256, ATT_BWD_SMEM, stream>>>(tmQ, tmD, p, acc);
-    else attn_bwd_kernel<false><<<grid, 256, ATT_BWD_SMEM, stream>>>(tmQ, tmD, p, acc);
+    if (di) UB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true>, grid, dim3(256), ATT_BWD_SMEM, stream, 1, tmQ, tmD, p, acc));
+    else UB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false>, grid, dim3(256), ATT_BWD_SMEM, stream, 1, tmQ, tmD, p, acc));
   }
   UB_CHECK_CUDA(cudaGetLastError());
   if (multi) {
     ProfScope ps(stream);
-    if (di) attn_dq_convert_kernel<true><<<a.batch, 256, 0, stream>>>(acc, a.dqkv, a.cu_seqlens, a.hidden);
-    else attn_dq_convert_kernel<false><<<a.batch, 256, 0, stream>>>(acc, a.dqkv, a.cu_seqlens, a.hidden);
+    if (di) UB_CHECK_CUDA(launch_pdl(attn_dq_convert_kernel<true>, dim3(a.batch), dim3(256), 0, stream, 1, static_cast<const float*>(acc), a.dqkv, a.cu_seqlens, a.hidden));
+    else UB_CHECK_CUDA(launch_pdl(attn_dq_convert_kernel<false>, dim3(a.batch), dim3(256), 0, stream, 1, static_cast<const float*>(acc), a.dqkv, a.cu_seqlens, a.hidden));
     UB_CHECK_CUDA(cudaGetLastError());
   }
   return 0;

@@ -59,6 +59,8 @@ struct PrepParams {
 };
 
 __global__ void embed_prep_kernel(const PrepParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= p.T) return;
   const int flat = p.pack_idx[t];
@@ -91,6 +93,8 @@ __global__ void __launch_bounds__(256)
 embed_gather_cast_kernel(const TIn* __restrict__ feat, const int* __restrict__ img_src,
                          const int* __restrict__ mask_flag, const void* __restrict__ mask_row_,
                          void* __restrict__ out_, int T, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   using T16 = typename Elem<kBF16>::T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -146,6 +150,8 @@ struct RowsParams {
 template <bool kBF16, int NV>
 __global__ void __launch_bounds__(256)
 embed_rows_fwd_kernel(const RowsParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   using T16 = typename Elem<kBF16>::T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + warp;

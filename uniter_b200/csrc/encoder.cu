@@ -77,7 +77,8 @@ static int check_desc(const ub200_encoder_desc* d, const char* who) {
 }
 
 static inline uint64_t rng_stream_of(const ub200_encoder_desc* d, int layer, int site) {
-  return (d->rng_offset << 20) | (static_cast<uint64_t>(layer) << 4) | static_cast<uint64_t>(site);
+  return (d->rng_offset << 20) | (static_cast<uint64_t>(layer + d->layer_offset) << 4) |
+         static_cast<uint64_t>(site);
 }
 enum { SITE_ATTN_PROBS = 1, SITE_ATTN_OUT = 2, SITE_FFN_OUT = 3 };
 

@@ -315,10 +315,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
+  pdl_launch_dependents();   // dependents may start their own prologue
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();                // the producing kernel has completed; its outputs are visible
   if (threadIdx.x == 0) UB_TRACE(1);
 
   if (warp == 0) {
@@ -468,11 +470,13 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tmem_alloc_2sm(tmem_ptr_smem, Cfg::TMEM_COLS);
     tmem_relinquish_2sm();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp == 0) {
     // ===================================================================== TMA producer (both CTAs)
@@ -584,21 +588,10 @@ static int launch_gemm(const GemmParams& p, const CUtensorMap& tmA, const CUtens
                                        Cfg::SMEM_BYTES));
     configured = true;
   }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   {
     ProfScope ps(stream);
-    UB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+    UB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, kCluster,
+                             tmA, tmB, p));
   }
   return 0;
 }

@@ -43,6 +43,8 @@ template <bool kBF16>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const void* __restrict__ x_, const void* __restrict__ gamma_,
               const void* __restrict__ beta_, void* __restrict__ y_, int rows, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   using T16 = typename Elem<kBF16>::T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -112,6 +114,8 @@ struct LnBwdParams {
 template <bool kBF16, int NV>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const LnBwdParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   using T16 = typename Elem<kBF16>::T;
   __shared__ float red[3][8][32 * 8 + 1];  // [quantity][warp][lane*8+e] for one vector slot
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -271,6 +275,8 @@ template <int kDummy>
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
                    const int* __restrict__ idx, int rows, int vec_per_row) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
@@ -289,6 +295,8 @@ template <bool kBF16>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const void* __restrict__ x_, float* __restrict__ out, int rows, int N, int ld,
               int rows_per_cta) {
+  pdl_launch_dependents();
+  pdl_wait();
   using T16 = typename Elem<kBF16>::T;
   // CTA = 32 column-vectors (256 columns) x 8 row lanes
   __shared__ float red[8][256 + 1];
@@ -323,6 +331,8 @@ colsum_kernel(const void* __restrict__ x_, float* __restrict__ out, int rows, in
 template <bool kBF16>
 __global__ void __launch_bounds__(256)
 cvt_kernel(const float* __restrict__ src, void* __restrict__ dst_, long long n, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   using T16 = typename Elem<kBF16>::T;
   T16* dst = reinterpret_cast<T16*>(dst_);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -338,6 +348,8 @@ template <bool kBF16>
 __global__ void __launch_bounds__(256)
 add16_kernel(uint4* __restrict__ dst, const uint4* __restrict__ a, const uint4* __restrict__ b,
              long long nvec) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float x[8], y[8];
@@ -357,20 +369,20 @@ int launch_ln_fwd(int dtype, const void* x, const void* gamma, const void* beta,
                      LN_MAX_VEC * 256, H);
   const int grid = (rows + 7) / 8;
   ProfScope ps(stream);
-  if (dtype == UB200_BF16) ln_fwd_kernel<true><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, H);
-  else ln_fwd_kernel<false><<<grid, 256, 0, stream>>>(x, gamma, beta, y, rows, H);
+  if (dtype == UB200_BF16) UB_CHECK_CUDA(launch_pdl(ln_fwd_kernel<true>, dim3(grid), dim3(256), 0, stream, 1, x, gamma, beta, y, rows, H));
+  else UB_CHECK_CUDA(launch_pdl(ln_fwd_kernel<false>, dim3(grid), dim3(256), 0, stream, 1, x, gamma, beta, y, rows, H));
   UB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <bool kBF16>
-static void launch_ln_bwd_nv(const LnBwdParams& p, int grid, cudaStream_t stream) {
+static cudaError_t launch_ln_bwd_nv(const LnBwdParams& p, int grid, cudaStream_t stream) {
   const int nv = (p.H + 255) / 256;
   switch (nv) {
-    case 1: ln_bwd_kernel<kBF16, 1><<<grid, 256, 0, stream>>>(p); break;
-    case 2: ln_bwd_kernel<kBF16, 2><<<grid, 256, 0, stream>>>(p); break;
-    case 3: ln_bwd_kernel<kBF16, 3><<<grid, 256, 0, stream>>>(p); break;
-    default: ln_bwd_kernel<kBF16, 4><<<grid, 256, 0, stream>>>(p); break;
+    case 1: return launch_pdl(ln_bwd_kernel<kBF16, 1>, dim3(grid), dim3(256), 0, stream, 1, p);
+    case 2: return launch_pdl(ln_bwd_kernel<kBF16, 2>, dim3(grid), dim3(256), 0, stream, 1, p);
+    case 3: return launch_pdl(ln_bwd_kernel<kBF16, 3>, dim3(grid), dim3(256), 0, stream, 1, p);
+    default: return launch_pdl(ln_bwd_kernel<kBF16, 4>, dim3(grid), dim3(256), 0, stream, 1, p);
   }
 }
 
@@ -382,9 +394,8 @@ int launch_ln_bwd(int dtype, const LnBwdParams& p, cudaStream_t stream) {
   const int cap = num_sms();   // one wave, one CTA per SM
   if (grid > cap) grid = cap;
   ProfScope ps(stream);
-  if (dtype == UB200_BF16) launch_ln_bwd_nv<true>(p, grid, stream);
-  else launch_ln_bwd_nv<false>(p, grid, stream);
-  UB_CHECK_CUDA(cudaGetLastError());
+  if (dtype == UB200_BF16) UB_CHECK_CUDA(launch_ln_bwd_nv<true>(p, grid, stream));
+  else UB_CHECK_CUDA(launch_ln_bwd_nv<false>(p, grid, stream));
   return 0;
 }
 
@@ -409,8 +420,8 @@ int launch_colsum(int dtype, const void* x, float* out, int rows, int N, int ld,
   const int rpc = (rows + gy - 1) / gy;
   dim3 grid(gx, gy);
   ProfScope ps(stream);
-  if (dtype == UB200_BF16) colsum_kernel<true><<<grid, 256, 0, stream>>>(x, out, rows, N, ld, rpc);
-  else colsum_kernel<false><<<grid, 256, 0, stream>>>(x, out, rows, N, ld, rpc);
+  if (dtype == UB200_BF16) UB_CHECK_CUDA(launch_pdl(colsum_kernel<true>, grid, dim3(256), 0, stream, 1, x, out, rows, N, ld, rpc));
+  else UB_CHECK_CUDA(launch_pdl(colsum_kernel<false>, grid, dim3(256), 0, stream, 1, x, out, rows, N, ld, rpc));
   UB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -423,9 +434,9 @@ int launch_cvt(int dtype, const float* src, void* dst, long long n, int accumula
   if (blocks > cap) blocks = cap;
   ProfScope ps(stream);
   if (dtype == UB200_BF16)
-    cvt_kernel<true><<<static_cast<int>(blocks), 256, 0, stream>>>(src, dst, n, accumulate);
+    UB_CHECK_CUDA(launch_pdl(cvt_kernel<true>, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, 1, src, dst, n, accumulate));
   else
-    cvt_kernel<false><<<static_cast<int>(blocks), 256, 0, stream>>>(src, dst, n, accumulate);
+    UB_CHECK_CUDA(launch_pdl(cvt_kernel<false>, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, 1, src, dst, n, accumulate));
   UB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

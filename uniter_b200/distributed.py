@@ -37,11 +37,26 @@ def broadcast_parameters(model, root=0):
 class GradientReducer:
     """Average gradients over ranks after backward: arena in place + one bucket for the rest."""
 
-    def __init__(self, model):
+    def __init__(self, model, overlap_chunks=4):
         self.model = model
         self.encoders = [m for m in model.modules() if isinstance(m, UniterModel)]
         self._others = None
         self._flat = None
+        self.overlap_chunks = overlap_chunks
+        self._pending = []
+        self._reduced = set()
+        self._comm_stream = None
+
+    # ---- overlap: called by _EncoderStack.backward after the kernels of layers [lo, hi) are enqueued
+    def _on_chunk(self, enc, lo, hi):
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream()
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self._comm_stream):
+            self._comm_stream.wait_event(ev)
+            self._pending.append(_avg_all_reduce(enc.arena_slice(lo, hi), async_op=True))
+        self._reduced.add(id(enc))
 
     def _arena_param_ids(self):
         ids = set()
@@ -54,8 +69,12 @@ class GradientReducer:
     def reduce(self):
         works = []
         arena_ids = self._arena_param_ids()
+        works += self._pending
+        self._pending = []
         for enc in self.encoders:
-            works.append(_avg_all_reduce(enc.grad_arena(), async_op=True))
+            if id(enc) not in self._reduced:      # not already reduced chunk-wise during backward
+                works.append(_avg_all_reduce(enc.grad_arena(), async_op=True))
+        self._reduced = set()
         # parameters outside the arena (tied weights appear once: parameters() de-duplicates)
         others = [p for p in self.model.parameters() if p.grad is not None and id(p) not in arena_ids]
         if others:
@@ -74,5 +93,17 @@ class GradientReducer:
                 w.wait()
 
     def backward_and_reduce(self, loss):
-        loss.backward()
+        """loss.backward() with the encoder gradients all-reduced chunk by chunk while the rest of
+        the backward is still running (replaces the non-overlapped Horovod call of
+        train_vqa.py:193-199), then the remaining parameters."""
+        overlap = self.overlap_chunks > 1 and dist.get_backend() == "nccl"
+        if overlap:
+            for enc in self.encoders:
+                enc._bwd_chunk_hook = self._on_chunk
+                enc._bwd_chunks = self.overlap_chunks
+        try:
+            loss.backward()
+        finally:
+            for enc in self.encoders:
+                enc._bwd_chunk_hook = None
         self.reduce()

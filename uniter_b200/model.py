@@ -283,7 +283,8 @@ class _EncoderDesc(C.Structure):
                 ("num_layers", C.c_int32), ("dtype", C.c_int32), ("batch", C.c_int32),
                 ("total_tokens", C.c_int32), ("max_seqlen", C.c_int32),
                 ("cu_seqlens", C.c_void_p), ("hidden_dropout_p", C.c_float),
-                ("attn_dropout_p", C.c_float), ("rng_seed", C.c_uint64), ("rng_offset", C.c_uint64)]
+                ("attn_dropout_p", C.c_float), ("rng_seed", C.c_uint64), ("rng_offset", C.c_uint64),
+                ("layer_offset", C.c_int32)]
 
 
 _lib_ready = False
@@ -543,20 +544,42 @@ class _EncoderStack(torch.autograd.Function):
         NL = desc.num_layers
         T, H = x.shape
         grad_out = grad_out.contiguous()
-        if ctx.want_all:
-            d_ptrs = (C.c_void_p * NL)(*[grad_out[l].data_ptr() for l in range(NL)])
-        else:
-            d_ptrs = (C.c_void_p * NL)(*([None] * (NL - 1) + [grad_out.data_ptr()]))
         grads, accumulate = model._grad_table()
+        weights = model._weight_table()
         scratch = torch.empty(lib.ub200_encoder_bwd_scratch_bytes(C.byref(desc)), device=x.device,
                               dtype=torch.uint8)
-        dx = torch.empty_like(x)
-        _lib.check(lib.ub200_encoder_bwd(C.byref(desc), model._weight_table(), grads, x.data_ptr(),
-                                         ctx.out_ptrs, act.data_ptr(), d_ptrs, dx.data_ptr(),
-                                         scratch.data_ptr(), 1 if accumulate else 0,
-                                         _lib.current_stream()))
-        model._finish_grads(accumulate)
-        return dx, None, None, None, None, None
+        act_bytes = lib.ub200_encoder_act_bytes_per_layer(C.byref(desc))
+        stream = _lib.current_stream()
+        hook = getattr(model, "_bwd_chunk_hook", None)
+        nchunks = max(1, min(NL, int(getattr(model, "_bwd_chunks", 1)))) if hook is not None else 1
+        bounds = [round(i * NL / nchunks) for i in range(nchunks + 1)]
+        # the backward is issued in chunks of layers (top chunk first) so that a data-parallel
+        # reducer can start all-reducing a chunk's gradients while the next chunk is computing
+        dtop = grad_out[NL - 1] if ctx.want_all else grad_out
+        for ci in range(nchunks - 1, -1, -1):
+            lo, hi = bounds[ci], bounds[ci + 1]
+            n = hi - lo
+            d = _EncoderDesc.from_buffer_copy(desc)
+            d.num_layers, d.layer_offset = n, lo
+            d_ptrs = (C.c_void_p * n)()
+            if ctx.want_all:
+                for l in range(lo, hi - 1):
+                    d_ptrs[l - lo] = grad_out[l].data_ptr()
+            d_ptrs[n - 1] = dtop.data_ptr()
+            x_in = x if lo == 0 else outs[lo - 1]
+            dx = torch.empty_like(x)
+            out_ptrs = (C.c_void_p * n)(*[outs[l].data_ptr() for l in range(lo, hi)])
+            _lib.check(lib.ub200_encoder_bwd(
+                C.byref(d), C.byref(weights[lo]), C.byref(grads[lo]), x_in.data_ptr(), out_ptrs,
+                act.data_ptr() + lo * act_bytes, d_ptrs, dx.data_ptr(), scratch.data_ptr(),
+                1 if accumulate else 0, stream))
+            if lo > 0 and ctx.want_all:
+                dx = dx + grad_out[lo - 1]
+            dtop = dx
+            model._finish_grads(accumulate, lo, hi)
+            if hook is not None:
+                hook(model, lo, hi)
+        return dtop, None, None, None, None, None
 
 
 # ============================================================================ the model
@@ -685,24 +708,34 @@ class UniterModel(UniterPreTrainedModel):
         A["small32"].zero_()
         return A["gtable"], accumulate
 
-    def _finish_grads(self, accumulate):
+    def _finish_grads(self, accumulate, lo=0, hi=None):
+        """fp32 -> 16-bit for the small (bias / LayerNorm) gradients of layers [lo, hi) and, on a
+        fresh backward, attach the arena views as the parameters' .grad."""
         lib = _bind()
         A = self._arena
         NL = self.config.num_hidden_layers
+        hi = NL if hi is None else hi
         flat, small32, n = A["flat"], A["small32"], A["small_n"]
         dt = _lib.dtype_code(flat.dtype)
         stream = _lib.current_stream()
-        for i in range(NL):
+        for i in range(lo, hi):
             dst = flat[i * A["per_layer"] + A["big_n"]:(i + 1) * A["per_layer"]]
             _lib.check(lib.ub200_cvt_from_f32(small32[i * n:(i + 1) * n].data_ptr(), dst.data_ptr(), n,
                                               1 if accumulate else 0, dt, stream))
-        if not accumulate:
+        if not accumulate and lo == 0:
             for p, v in A["views"]:
                 if p.requires_grad:
                     if p.grad is None:
                         p.grad = v
-                    else:          # a foreign gradient tensor is already there: add into it
+                    elif p.grad.data_ptr() != v.data_ptr():   # a foreign gradient tensor: add into it
                         p.grad.add_(v)
+
+    def arena_slice(self, lo, hi):
+        """Flat gradient slice of encoder layers [lo, hi) (contiguous)."""
+        if self._arena is None:
+            self._build_arena()
+        per = self._arena["per_layer"]
+        return self._arena["flat"][lo * per:hi * per]
 
     # ------------------------------------------------------------------ embeddings (reference API)
     def _compute_txt_embeddings(self, input_ids, position_ids, txt_type_ids=None):
