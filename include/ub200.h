@@ -104,7 +104,7 @@ typedef struct {
   float dropout_p;         /* 0 <= p < 1 */
   uint64_t rng_seed;       /* Philox key */
   uint64_t rng_stream;     /* distinguishes dropout sites / layers / steps */
-  int32_t tile_n;          /* 0 = heuristic, else force 64 / 128 / 256 */
+  int32_t tile_n;          /* 0 = heuristic, else force 64 / 128 / 192 / 256 */
   int32_t max_ctas;        /* 0 = one CTA per SM */
   int32_t cluster;         /* 0 = heuristic, 1 = single CTAs, 2 = 2-CTA clusters sharing B by
                               TMA multicast */

@@ -17,7 +17,7 @@ def _close(got, ref, tol, what):
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("shape", [(128, 128, 64), (333, 768, 768), (3451, 2304, 768), (777, 768, 3072),
                                    (1, 64, 64), (130, 8, 72)])
-@pytest.mark.parametrize("tn,cluster", [(0, 0), (64, 1), (128, 1), (256, 1), (128, 2), (256, 2)])
+@pytest.mark.parametrize("tn,cluster", [(0, 0), (64, 1), (128, 1), (192, 1), (256, 1), (128, 2), (256, 2)])
 def test_gemm_operand_majors(dtype, shape, tn, cluster):
     from uniter_b200 import ops
     M, N, K = shape

@@ -139,7 +139,7 @@ def main():
         a = torch.randn((K, M) if am else (M, K), device=dev).to(torch.bfloat16)
         b = torch.randn((K, N) if bm else (N, K), device=dev).to(torch.bfloat16)
         res = []
-        for tn, cl in ((0, 0), (64, 1), (128, 1), (256, 1), (128, 2), (256, 2)):
+        for tn, cl in ((0, 0), (128, 1), (192, 1), (256, 1), (128, 2), (256, 2)):
             us = tm(lambda: ops.gemm(a, b, a_major=am, b_major=bm, tile_n=tn, cluster=cl))
             res.append("tn%d/c%d %.1fus %.0fTF" % (tn, cl, us, 2.0 * M * N * K / us / 1e6))
         aa = a.t() if am else a

@@ -61,18 +61,25 @@ __device__ __forceinline__ void st_swz128(uint8_t* base, int r, int col8, uint4 
 
 template <bool kBF16>
 __global__ void __launch_bounds__(128)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmQKV64,
+                const AttnParams p) {
   pdl_launch_dependents();
   pdl_wait();   // cu_seqlens / qkv come from preceding kernels
-  const int b = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
+  const int b = blockIdx.z, qt = blockIdx.x;
   const int seq0 = p.cu_seqlens[b];
   const int S = p.cu_seqlens[b + 1] - seq0;
   if (qt * ATT_BM >= S) return;  // whole CTA exits together, before any barrier / TMEM use
-  const int nkv = (S + ATT_BN - 1) / ATT_BN;
+  // Head-pair packing: a sequence of <= 64 tokens fills only half of the 128-row MMA tile, so
+  // one CTA carries TWO heads: rows 0-63 = head h0, rows 64-127 = head h0+1, keys likewise.
+  // S = Q K^T over the 128 stacked keys is block diagonal in what matters; the off-diagonal
+  // blocks of P are written as zeros so that O = P V stays one 128-key contraction.
+  const bool pair = (S <= 64) && ((p.nheads & 1) == 0);
+  if (pair && static_cast<int>(blockIdx.y) >= p.nheads / 2) return;
+  const int h0 = pair ? 2 * blockIdx.y : blockIdx.y;
+  const int nkv = (S + ATT_BN - 1) / ATT_BN;   // 1 in pair mode
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sK = smem + ATT_TILE;
   uint8_t* sV = smem + 2 * ATT_TILE;
@@ -81,9 +88,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   uint64_t* bar_mma = bar_load + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
     tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmQKV64);
     mbar_init(bar_load, 1);
     mbar_init(bar_mma, 1);
     fence_barrier_init();
@@ -100,7 +108,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   const uint32_t tO = tmem + 128;    // 64 fp32 columns
   const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
 
-  const int qrow = qt * ATT_BM + tid;          // query index inside the sequence
+  // this thread's query row: (head, position in the sequence, first key column of its block)
+  const int half = pair ? (tid >> 6) : 0;
+  const int head = h0 + half;
+  const int qrow = pair ? (tid & 63) : qt * ATT_BM + tid;
+  const int kcol0 = half * 64;
   const bool q_ok = qrow < S;
   const int bh = b * p.nheads + head;
   const float c = p.scale * 1.4426950408889634f;  // scale * log2(e)
@@ -109,14 +121,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   // ---------------------------------------------------------------- sweep 1: row max
   float m = -INFINITY, l = 0.f;
   for (int j = 0; j < nkv; ++j) {
-    const int kv_len = min(ATT_BN, S - j * ATT_BN);
-    const int n_pad = (kv_len + 15) & ~15;
+    const int kv_len = pair ? S : min(ATT_BN, S - j * ATT_BN);
+    const int n_pad = pair ? ATT_BN : ((kv_len + 15) & ~15);
     if (tid == 0) {
-      const bool with_v = (nkv == 1);
-      mbar_expect_tx(bar_load, (j == 0 ? ATT_TILE : 0) + ATT_TILE + (with_v ? ATT_TILE : 0));
-      if (j == 0) tma_load_2d(sQ, &tmQKV, bar_load, head * ATT_D, seq0 + qt * ATT_BM);
-      tma_load_2d(sK, &tmQKV, bar_load, p.H + head * ATT_D, seq0 + j * ATT_BN);
-      if (with_v) tma_load_2d(sV, &tmQKV, bar_load, 2 * p.H + head * ATT_D, seq0 + j * ATT_BN);
+      if (pair) {
+        mbar_expect_tx(bar_load, 3 * ATT_TILE);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          tma_load_2d(sQ + hh * (ATT_TILE / 2), &tmQKV64, bar_load, (h0 + hh) * ATT_D, seq0);
+          tma_load_2d(sK + hh * (ATT_TILE / 2), &tmQKV64, bar_load, p.H + (h0 + hh) * ATT_D, seq0);
+          tma_load_2d(sV + hh * (ATT_TILE / 2), &tmQKV64, bar_load, 2 * p.H + (h0 + hh) * ATT_D, seq0);
+        }
+      } else {
+        const bool with_v = (nkv == 1);
+        mbar_expect_tx(bar_load, (j == 0 ? ATT_TILE : 0) + ATT_TILE + (with_v ? ATT_TILE : 0));
+        if (j == 0) tma_load_2d(sQ, &tmQKV, bar_load, head * ATT_D, seq0 + qt * ATT_BM);
+        tma_load_2d(sK, &tmQKV, bar_load, p.H + head * ATT_D, seq0 + j * ATT_BN);
+        if (with_v) tma_load_2d(sV, &tmQKV, bar_load, 2 * p.H + head * ATT_D, seq0 + j * ATT_BN);
+      }
       mbar_wait(bar_load, ph_load);
       tc_fence_after();
       const uint32_t idesc = umma_idesc(kBF16 ? 1 : 0, 0, 0, ATT_BM, n_pad);
@@ -132,7 +154,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     tc_fence_after();
     for (int cc = 0; cc * 32 < kv_len; ++cc) {
       uint32_t r[32];
-      tmem_ld32(tS + lane_off + cc * 32, r);
+      tmem_ld32(tS + lane_off + kcol0 + cc * 32, r);
       tmem_ld_wait();
       if ((cc + 1) * 32 <= kv_len) {
 #pragma unroll
@@ -153,8 +175,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 
   // ---------------------------------------------------------------- sweep 2: P and O = P V
   for (int j = 0; j < nkv; ++j) {
-    const int kv_len = min(ATT_BN, S - j * ATT_BN);
-    const int n_pad = (kv_len + 15) & ~15;
+    const int kv_len = pair ? S : min(ATT_BN, S - j * ATT_BN);
+    const int n_pad = pair ? ATT_BN : ((kv_len + 15) & ~15);
     if (nkv > 1) {
       if (tid == 0) {
         mbar_expect_tx(bar_load, 2 * ATT_TILE);
@@ -175,21 +197,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       tc_fence_after();
     }
     // probabilities -> 16-bit -> swizzled smem (A operand of P.V)
-    for (int cc = 0; cc * 32 < n_pad; ++cc) {
+    const int own_pad = pair ? 64 : n_pad;     // columns of this row's own block
+    for (int cc = 0; cc * 32 < own_pad; ++cc) {
       uint32_t r[32];
-      tmem_ld32(tS + lane_off + cc * 32, r);
+      tmem_ld32(tS + lane_off + kcol0 + cc * 32, r);
       tmem_ld_wait();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const int key0 = cc * 32 + g * 8;  // within this KV block
-        if (key0 >= n_pad) break;
+        const int key0 = cc * 32 + g * 8;  // within this row's key block
+        if (key0 >= own_pad) break;
         float pv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float s = __uint_as_float(r[g * 8 + i]);
+          const float sc = __uint_as_float(r[g * 8 + i]);
           // unnormalised probability exp(scale*(s - max)) in (0, 1]; O is divided by the row sum
           // at the end (the 1/l factor commutes with dropout and with P.V)
-          pv[i] = (key0 + i < kv_len) ? ex2_approx(fmaf(s, c, -mc)) : 0.f;
+          pv[i] = (key0 + i < kv_len) ? ex2_approx(fmaf(sc, c, -mc)) : 0.f;
           l += pv[i];
         }
         if (p.drop_thr16) {
@@ -208,8 +231,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         u.y = Elem<kBF16>::pack(pv[2], pv[3]);
         u.z = Elem<kBF16>::pack(pv[4], pv[5]);
         u.w = Elem<kBF16>::pack(pv[6], pv[7]);
-        st_swz128(sP, tid, key0, u);
+        st_swz128(sP, tid, kcol0 + key0, u);
       }
+    }
+    if (pair) {   // the other head's 64 key columns of this row: exact zeros
+#pragma unroll
+      for (int g = 0; g < 8; ++g) st_swz128(sP, tid, (64 - kcol0) + g * 8, make_uint4(0, 0, 0, 0));
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -276,22 +303,27 @@ constexpr int ATT_FWD_SMEM = 5 * ATT_TILE + 64 + 1024;
 template <bool kBF16>
 __global__ void __launch_bounds__(256)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const __grid_constant__ CUtensorMap tmQKV64, const __grid_constant__ CUtensorMap tmDO64,
                 const AttnParams p, float* dq_accum) {
   using T16 = typename Elem<kBF16>::T;
   pdl_launch_dependents();
   pdl_wait();
-  const int b = blockIdx.z, head = blockIdx.y, j = blockIdx.x;
+  const int b = blockIdx.z, j = blockIdx.x;
   const int seq0 = p.cu_seqlens[b];
   const int S = p.cu_seqlens[b + 1] - seq0;
   if (j * ATT_BN >= S) return;
+  // head-pair packing for short sequences (see attn_fwd_kernel): rows / keys 0-63 belong to head
+  // h0, 64-127 to head h0+1; P and dS are block diagonal with exact zeros off the diagonal.
+  const bool pair = (S <= 64) && ((p.nheads & 1) == 0);
+  if (pair && static_cast<int>(blockIdx.y) >= p.nheads / 2) return;
+  const int h0 = pair ? 2 * blockIdx.y : blockIdx.y;
   const int nq = (S + ATT_BM - 1) / ATT_BM;
   const int nkv = (S + ATT_BN - 1) / ATT_BN;
-  const int kv_len = min(ATT_BN, S - j * ATT_BN);
-  const int n_pad = (kv_len + 15) & ~15;
+  const int kv_len = pair ? S : min(ATT_BN, S - j * ATT_BN);
+  const int n_pad = pair ? ATT_BN : ((kv_len + 15) & ~15);
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sdO = smem + ATT_TILE;
   uint8_t* sK = smem + 2 * ATT_TILE;
@@ -307,6 +339,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row_t = tid & 127;
   const int chalf = tid >> 7;
+  const int half = pair ? (row_t >> 6) : 0;
+  const int head = h0 + half;
+  const int kcol0 = half * 64;
   if (tid == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
@@ -331,16 +366,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   for (int i = 0; i < nq; ++i) {
     const int q_len = min(ATT_BM, S - i * ATT_BM);
-    const int q_pad = (q_len + 15) & ~15;
-    const int qrow = i * ATT_BM + row_t;
+    const int q_pad = pair ? ATT_BM : ((q_len + 15) & ~15);
+    const int qrow = pair ? (row_t & 63) : i * ATT_BM + row_t;
     const bool q_ok = qrow < S;
     if (tid == 0) {
-      mbar_expect_tx(bar_load, (i == 0 ? 4 : 2) * ATT_TILE);
-      tma_load_2d(sQ, &tmQKV, bar_load, head * ATT_D, seq0 + i * ATT_BM);
-      tma_load_2d(sdO, &tmDO, bar_load, head * ATT_D, seq0 + i * ATT_BM);
-      if (i == 0) {
-        tma_load_2d(sK, &tmQKV, bar_load, p.H + head * ATT_D, seq0 + j * ATT_BN);
-        tma_load_2d(sV, &tmQKV, bar_load, 2 * p.H + head * ATT_D, seq0 + j * ATT_BN);
+      if (pair) {
+        mbar_expect_tx(bar_load, 4 * ATT_TILE);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int o = hh * (ATT_TILE / 2);
+          tma_load_2d(sQ + o, &tmQKV64, bar_load, (h0 + hh) * ATT_D, seq0);
+          tma_load_2d(sdO + o, &tmDO64, bar_load, (h0 + hh) * ATT_D, seq0);
+          tma_load_2d(sK + o, &tmQKV64, bar_load, p.H + (h0 + hh) * ATT_D, seq0);
+          tma_load_2d(sV + o, &tmQKV64, bar_load, 2 * p.H + (h0 + hh) * ATT_D, seq0);
+        }
+      } else {
+        mbar_expect_tx(bar_load, (i == 0 ? 4 : 2) * ATT_TILE);
+        tma_load_2d(sQ, &tmQKV, bar_load, head * ATT_D, seq0 + i * ATT_BM);
+        tma_load_2d(sdO, &tmDO, bar_load, head * ATT_D, seq0 + i * ATT_BM);
+        if (i == 0) {
+          tma_load_2d(sK, &tmQKV, bar_load, p.H + head * ATT_D, seq0 + j * ATT_BN);
+          tma_load_2d(sV, &tmQKV, bar_load, 2 * p.H + head * ATT_D, seq0 + j * ATT_BN);
+        }
       }
       mbar_wait(bar_load, ph_load);
       tc_fence_after();
@@ -379,15 +426,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     ph_mma ^= 1;
     tc_fence_after();
 
-    for (int cc = chalf * 2; cc < chalf * 2 + 2 && cc * 32 < n_pad; ++cc) {
+    // 32-column blocks of this thread: pair mode -> one block of the row's own 64 columns (and
+    // zero-fill of the matching block of the other head); else two of the up to four blocks.
+    const int cc_begin = pair ? (half * 2 + chalf) : chalf * 2;
+    const int cc_end = pair ? cc_begin + 1 : chalf * 2 + 2;
+    for (int cc = cc_begin; cc < cc_end && cc * 32 < n_pad; ++cc) {
       uint32_t rs[32], rp[32];
       tmem_ld32(tS + lane_off + cc * 32, rs);
       tmem_ld32(tP + lane_off + cc * 32, rp);
       tmem_ld_wait();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const int key0 = cc * 32 + g * 8;
-        if (key0 >= n_pad) break;
+        const int col0 = cc * 32 + g * 8;          // column in the 128-wide tile
+        if (col0 >= n_pad) break;
+        const int key0 = col0 - kcol0;             // key index inside this KV block
         float pd[8], ds[8];
         uint4 rnd = make_uint4(0, 0, 0, 0);
         if (p.drop_thr16) {
@@ -413,10 +465,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         uint4 u;
         u.x = Elem<kBF16>::pack(pd[0], pd[1]); u.y = Elem<kBF16>::pack(pd[2], pd[3]);
         u.z = Elem<kBF16>::pack(pd[4], pd[5]); u.w = Elem<kBF16>::pack(pd[6], pd[7]);
-        st_swz128(sP, row_t, key0, u);
+        st_swz128(sP, row_t, col0, u);
         u.x = Elem<kBF16>::pack(ds[0], ds[1]); u.y = Elem<kBF16>::pack(ds[2], ds[3]);
         u.z = Elem<kBF16>::pack(ds[4], ds[5]); u.w = Elem<kBF16>::pack(ds[6], ds[7]);
-        st_swz128(sDS, row_t, key0, u);
+        st_swz128(sDS, row_t, col0, u);
+      }
+    }
+    if (pair) {   // exact zeros in the other head's key columns of this row
+      const int zc = ((1 - half) * 2 + chalf) * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        st_swz128(sP, row_t, zc + g * 8, make_uint4(0, 0, 0, 0));
+        st_swz128(sDS, row_t, zc + g * 8, make_uint4(0, 0, 0, 0));
       }
     }
     fence_proxy_async_smem();
@@ -483,7 +543,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   // dK_j, dV_j out (rows = keys)
   {
-    const int key = j * ATT_BN + row_t;
+    const int key = pair ? (row_t & 63) : j * ATT_BN + row_t;
     const bool k_ok = key < S;
     T16* outk = reinterpret_cast<T16*>(p.dqkv) + static_cast<size_t>(seq0 + key) * (3 * p.H) +
                 p.H + head * ATT_D;
@@ -560,9 +620,11 @@ extern "C" int ub200_attn_fwd(const ub200_attn_args* args, ub200_stream_t stream
   UB_CHECK_ARG(a.dtype == UB200_F16 || a.dtype == UB200_BF16, "attn_fwd: bad dtype");
   UB_CHECK_ARG(a.dropout_p >= 0.f && a.dropout_p < 1.f, "attn_fwd: dropout_p out of range");
 
-  CUtensorMap tm;
+  CUtensorMap tm, tm64;
   int rc = make_tma_2d(&tm, a.qkv, a.dtype, a.total_tokens, 3 * a.hidden, 3 * a.hidden, ATT_BM,
                        ATT_D);
+  if (rc) return rc;
+  rc = make_tma_2d(&tm64, a.qkv, a.dtype, a.total_tokens, 3 * a.hidden, 3 * a.hidden, 64, ATT_D);
   if (rc) return rc;
   AttnParams p{};
   p.cu_seqlens = a.cu_seqlens;
@@ -591,7 +653,7 @@ extern "C" int ub200_attn_fwd(const ub200_attn_args* args, ub200_stream_t stream
       configured[1] = true;
     }
     ProfScope ps(stream);
-    UB_CHECK_CUDA(launch_pdl(attn_fwd_kernel<true>, grid, dim3(128), ATT_FWD_SMEM, stream, 1, tm, p));
+    UB_CHECK_CUDA(launch_pdl(attn_fwd_kernel<true>, grid, dim3(128), ATT_FWD_SMEM, stream, 1, tm, tm64, p));
   } else {
     if (!configured[0]) {
       UB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>,
@@ -599,7 +661,7 @@ extern "C" int ub200_attn_fwd(const ub200_attn_args* args, ub200_stream_t stream
       configured[0] = true;
     }
     ProfScope ps(stream);
-    UB_CHECK_CUDA(launch_pdl(attn_fwd_kernel<false>, grid, dim3(128), ATT_FWD_SMEM, stream, 1, tm, p));
+    UB_CHECK_CUDA(launch_pdl(attn_fwd_kernel<false>, grid, dim3(128), ATT_FWD_SMEM, stream, 1, tm, tm64, p));
   }
   UB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -626,10 +688,14 @@ extern "C" int ub200_attn_bwd(const ub200_attn_args* args, ub200_stream_t stream
   const bool multi = a.max_seqlen > ATT_BN;
   UB_CHECK_ARG(!multi || a.workspace, "attn_bwd: max_seqlen > 128 needs the dQ workspace");
 
-  CUtensorMap tmQ, tmD;
+  CUtensorMap tmQ, tmD, tmQ64, tmD64;
   int rc = make_tma_2d(&tmQ, a.qkv, a.dtype, a.total_tokens, 3 * a.hidden, 3 * a.hidden, ATT_BM, ATT_D);
   if (rc) return rc;
   rc = make_tma_2d(&tmD, a.dctx, a.dtype, a.total_tokens, a.hidden, a.hidden, ATT_BM, ATT_D);
+  if (rc) return rc;
+  rc = make_tma_2d(&tmQ64, a.qkv, a.dtype, a.total_tokens, 3 * a.hidden, 3 * a.hidden, 64, ATT_D);
+  if (rc) return rc;
+  rc = make_tma_2d(&tmD64, a.dctx, a.dtype, a.total_tokens, a.hidden, a.hidden, 64, ATT_D);
   if (rc) return rc;
   AttnParams p{};
   p.cu_seqlens = a.cu_seqlens;
@@ -664,8 +730,8 @@ extern "C" int ub200_attn_bwd(const ub200_attn_args* args, ub200_stream_t stream
   }
   {
     ProfScope ps(stream);
-    if (di) UB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true>, grid, dim3(256), ATT_BWD_SMEM, stream, 1, tmQ, tmD, p, acc));
-    else UB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false>, grid, dim3(256), ATT_BWD_SMEM, stream, 1, tmQ, tmD, p, acc));
+    if (di) UB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true>, grid, dim3(256), ATT_BWD_SMEM, stream, 1, tmQ, tmD, tmQ64, tmD64, p, acc));
+    else UB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false>, grid, dim3(256), ATT_BWD_SMEM, stream, 1, tmQ, tmD, tmQ64, tmD64, p, acc));
   }
   UB_CHECK_CUDA(cudaGetLastError());
   if (multi) {

@@ -10,25 +10,26 @@ int gemm_dispatch_bf16(int bn, int cluster, int a_major, int b_major, const Gemm
 int gemm_dispatch_f16(int bn, int cluster, int a_major, int b_major, const GemmParams& p,
                       const CUtensorMap& tmA, const CUtensorMap& tmB, int grid, cudaStream_t stream);
 
-// Pick (N tile, CTAs per tile) minimising waves x per-unit cost.  Per k-block a CTA is bound by
-// max(MMA issue = 2*BN cycles, smem traffic = 2 * (16 KB + BN*128 B / ctas) / 128 B per cycle:
-// TMA writes + UMMA operand reads); the epilogue / prologue of a tile adds a roughly fixed cost.
+// Pick (N tile, CTAs per tile) minimising  waves x k-blocks x cycles-per-k-block + exposed tail.
+// Cycles per k-block are MEASURED on B200 (K = 12288 sweep, mainloop only): they are far from
+// proportional to the tile width — 1-SM: ~421 + 1.27*BN (583 @128, 745 @256); 2-SM pair:
+// ~552 + 0.59*BN per 256-row pair tile (627 @128, 702 @256) — so fewer, wider tiles win until
+// wave quantisation bites.  The epilogue of the last tile (~25 cycles per column of width) and
+// a fixed launch / prologue cost are exposed once.
 static void pick_config(int M, int N, int K, int sms, int* bn_out, int* cluster_out) {
   const int tiles_m = (M + BM - 1) / BM;
   const int num_kb = (K + BK - 1) / BK;
-  const int cand[5][2] = {{256, 2}, {128, 2}, {256, 1}, {128, 1}, {64, 1}};
+  const int cand[6][2] = {{256, 2}, {128, 2}, {256, 1}, {192, 1}, {128, 1}, {64, 1}};
   double best = 1e30;
   *bn_out = 128; *cluster_out = 1;
-  for (int i = 0; i < 5; ++i) {
+  for (int i = 0; i < 6; ++i) {
     const int bn = cand[i][0], c = cand[i][1];
     if (c == 2 && tiles_m < 2) continue;
     const int units = ((tiles_m + c - 1) / c) * ((N + bn - 1) / bn);
     const int slots = sms / c;
     const int waves = (units + slots - 1) / slots;
-    const double load = 2.0 * (16384.0 + bn * 128.0 / c) / 128.0;
-    const double mma = 2.0 * bn;
-    const double per_tile = num_kb * (load > mma ? load : mma) + 1500.0 + 6.0 * bn;
-    const double cost = waves * per_tile;
+    const double per_kb = (c == 1) ? 421.0 + 1.27 * bn : 552.0 + 0.59 * bn;
+    const double cost = static_cast<double>(waves) * num_kb * per_kb + 25.0 * bn + 3000.0;
     if (cost < best - 1e-9) { best = cost; *bn_out = bn; *cluster_out = c; }
   }
 }
@@ -62,11 +63,11 @@ extern "C" int ub200_gemm(const ub200_gemm_args* args, ub200_stream_t stream_) {
   pick_config(a.M, a.N, a.K, sms, &bn, &cluster);
   if (a.tile_n) {
     bn = a.tile_n;
-    if (!a.cluster) cluster = (bn >= 128 && a.M > BM) ? 2 : 1;
+    if (!a.cluster) cluster = ((bn == 128 || bn == 256) && a.M > BM) ? 2 : 1;
   }
   if (a.cluster) cluster = a.cluster;
   UB_CHECK_ARG(cluster == 1 || cluster == 2, "gemm: cluster must be 0, 1 or 2 (got %d)", cluster);
-  UB_CHECK_ARG(!(cluster == 2 && bn == 64), "gemm: cluster 2 needs tile_n >= 128");
+  UB_CHECK_ARG(!(cluster == 2 && (bn == 64 || bn == 192)), "gemm: cluster 2 needs tile_n 128 or 256");
 
   CUtensorMap tmA, tmB;
   int rc;

@@ -47,7 +47,8 @@ struct GemmCfg {
   static constexpr int B_TILE_BYTES = BN / kCtas * BK * 2;   // per CTA
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN;
+  // two accumulators of BN fp32 columns; allocations must be a power of two >= 32
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
   static constexpr int BAR_BYTES = 256;
   // per epilogue warp: 32 x 33 fp32 transpose buffer (lane == row  ->  4 lanes per row)
   static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * 33 * 4;
@@ -639,9 +640,10 @@ int gemm_dispatch(int bn, int cluster, int a_major, int b_major, const GemmParam
   switch (bn) {
     case 64: return dispatch_major<64, kBF16, 1>(a_major, b_major, p, tmA, tmB, grid, stream);
     case 128: return dispatch_major<128, kBF16, 1>(a_major, b_major, p, tmA, tmB, grid, stream);
+    case 192: return dispatch_major<192, kBF16, 1>(a_major, b_major, p, tmA, tmB, grid, stream);
     case 256: return dispatch_major<256, kBF16, 1>(a_major, b_major, p, tmA, tmB, grid, stream);
   }
-  return set_error(UB200_EINVAL, "gemm: tile_n must be 0, 64, 128 or 256 (got %d)", bn);
+  return set_error(UB200_EINVAL, "gemm: tile_n must be 0, 64, 128, 192 or 256 (got %d)", bn);
 }
 
 }  // namespace ub

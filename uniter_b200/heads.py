@@ -68,11 +68,18 @@ class UniterForMLM(UniterPreTrainedModel):
         sequence_output = self.uniter(input_ids, batch["position_ids"], batch["img_feat"],
                                       batch["img_pos_feat"], batch["attn_masks"],
                                       batch["gather_index"], output_all_encoded_layers=False)
-        sequence_output = sequence_output[:, :input_ids.size(1), :]
-        mask = (txt_labels != -1)
-        masked_output = sequence_output[mask.unsqueeze(-1).expand_as(sequence_output)] \
-            .contiguous().view(-1, sequence_output.size(-1))
+        if "mlm_index" in batch:
+            # loader-provided flat positions of the masked tokens: static-shape gather, no sync
+            H = sequence_output.size(-1)
+            masked_output = sequence_output.reshape(-1, H).index_select(0, batch["mlm_index"])
+            targets = batch["mlm_targets"]
+        else:
+            sequence_output = sequence_output[:, :input_ids.size(1), :]
+            mask = (txt_labels != -1)
+            masked_output = sequence_output[mask.unsqueeze(-1).expand_as(sequence_output)] \
+                .contiguous().view(-1, sequence_output.size(-1))
+            targets = txt_labels[mask]
         prediction_scores = self.cls(masked_output)
         if compute_loss:
-            return F.cross_entropy(prediction_scores.float(), txt_labels[mask], reduction="none")
+            return F.cross_entropy(prediction_scores.float(), targets, reduction="none")
         return prediction_scores

@@ -321,15 +321,17 @@ _rng_offset = [0]
 _META_CACHE = {}
 
 
-def register_lengths(attention_mask_dev, lens_host):
+def register_lengths(attention_mask_dev, lens_host, prefix=False):
     """Tell the model the per-sample valid lengths of a device attention mask that the host
     already knows (the loader computed them before the H2D copy), so forward() does not have to
-    read them back.  Keyed by the mask tensor's address + version."""
+    read them back.  Keyed by the mask tensor's address + version.  `prefix=True` additionally
+    asserts that the mask is a prefix mask ([1]*S_b + [0]*(L-S_b), what every reference collate
+    emits, e.g. data/vqa.py:39,53): the pack indices are then computed arithmetically."""
     B, L = attention_mask_dev.shape
     key = (attention_mask_dev.data_ptr(), attention_mask_dev._version, B, L)
     if len(_META_CACHE) > 64:
         _META_CACHE.clear()
-    _META_CACHE[key[0]] = (key, {"lens_host": [int(v) for v in lens_host]})
+    _META_CACHE[key[0]] = (key, {"lens_host": [int(v) for v in lens_host], "prefix": bool(prefix)})
 
 
 # ============================================================================ autograd glue
@@ -776,18 +778,32 @@ class UniterModel(UniterPreTrainedModel):
         hit = _META_CACHE.get(key[0])
         if hit is not None and hit[0] == key and "cu_seqlens" in hit[1]:
             return hit[1]
-        am = attention_mask != 0
-        lens = am.sum(1)
-        if hit is not None and hit[0] == key:
-            lens_h = hit[1]["lens_host"]          # registered by the loader: no sync
-        else:
-            lens_h = lens.tolist()                # host sync (B integers)
-        T = int(sum(lens_h))
         dev = attention_mask.device
-        cu = torch.zeros(B + 1, device=dev, dtype=torch.int32)
-        cu[1:] = torch.cumsum(lens, 0)
-        # [T] -> b*L+j ; size is known from the host-side lengths, so no second sync
-        pack_idx = torch.nonzero_static(am.reshape(-1), size=T).squeeze(1).to(torch.int32)
+        registered = hit is not None and hit[0] == key
+        if registered and hit[1].get("prefix"):
+            # prefix masks with host-known lengths: everything from arithmetic, no device reads
+            lens_h = hit[1]["lens_host"]
+            T = int(sum(lens_h))
+            cu_h = [0]
+            for v in lens_h:
+                cu_h.append(cu_h[-1] + v)
+            meta_h = torch.tensor([cu_h, lens_h + [0]], dtype=torch.int64)
+            meta_d = meta_h.to(dev, non_blocking=True)
+            cu = meta_d[0].to(torch.int32)
+            row_b = torch.repeat_interleave(torch.arange(B, device=dev), meta_d[1, :B], output_size=T)
+            pack_idx = (torch.arange(T, device=dev) - meta_d[0][row_b] + row_b * L).to(torch.int32)
+        else:
+            am = attention_mask != 0
+            lens = am.sum(1)
+            if registered:
+                lens_h = hit[1]["lens_host"]          # registered by the loader: no sync
+            else:
+                lens_h = lens.tolist()                # host sync (B integers)
+            T = int(sum(lens_h))
+            cu = torch.zeros(B + 1, device=dev, dtype=torch.int32)
+            cu[1:] = torch.cumsum(lens, 0)
+            # [T] -> b*L+j ; size is known from the host-side lengths, so no second sync
+            pack_idx = torch.nonzero_static(am.reshape(-1), size=T).squeeze(1).to(torch.int32)
         unpack_idx = torch.full((B * L,), -1, device=dev, dtype=torch.int32)
         unpack_idx[pack_idx.long()] = torch.arange(T, device=dev, dtype=torch.int32)
         meta = dict(batch=B, L=L, total=T, max_seqlen=max(lens_h) if lens_h else 0,

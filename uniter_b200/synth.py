@@ -67,6 +67,12 @@ def synth_batch(batch_size, tl_lo, tl_hi, nbb_lo, nbb_hi, seed, img_dim=2048, vo
     }
     if mlm_prob > 0:
         batch["txt_labels"] = txt_labels
+        # host-side compaction of the masked positions (flat index b * L + j into the encoder's
+        # [B, L] output): lets the MLM head gather its rows with a static shape instead of the
+        # boolean-mask indexing of model/pretrain.py:129-133, which costs a device sync per step
+        pos = (txt_labels != -1).nonzero(as_tuple=False)
+        batch["mlm_index"] = (pos[:, 0] * L + pos[:, 1]).contiguous()
+        batch["mlm_targets"] = txt_labels[pos[:, 0], pos[:, 1]].contiguous()
     return batch
 
 
