@@ -328,7 +328,7 @@ def main():
         lib.ub200_profile_enable(0)
         names = {0: "gather/cvt", 1: "qkv_gemm", 2: "attn_fwd", 3: "attnout_gemm", 4: "ln1_fwd",
                  5: "ffn1_gemm", 6: "ffn2_gemm", 7: "ln2_fwd", 8: "ln2_bwd", 9: "ffn2_dgrad",
-                 10: "ffn2_wgrad", 11: "ffn1_dgrad", 12: "ffn1_wgrad", 13: "ln1_bwd",
+                 10: "wgrad_grouped(4)", 11: "ffn1_dgrad", 12: "ffn1_wgrad", 13: "ln1_bwd",
                  14: "attnout_dgrad", 15: "attnout_wgrad", 16: "attn_bwd", 17: "colsum",
                  18: "qkv_dgrad", 19: "qkv_wgrad", 20: "grad_add"}
         breakdown = {names[i]: {"ms_per_step": round(ms_arr[i] / psteps, 4), "launches": cnt_arr[i] // psteps}

@@ -112,6 +112,11 @@ typedef struct {
 
 int ub200_gemm(const ub200_gemm_args* args, ub200_stream_t stream);
 
+/* Up to 4 weight-gradient GEMMs (a_major = b_major = 1, same K / dtype, epilogue 0 or
+ * UB200_EPI_ACCUM) as ONE persistent launch: the autograd mirror of the four nn.Linear modules of
+ * a BertLayer (model/layer.py:76-78,112,140,153), issued once at the end of the layer's backward. */
+int ub200_gemm_grouped(const ub200_gemm_args* args, int32_t count, ub200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused variable-length multi-head self-attention (head_dim 64), forward and backward.
  *

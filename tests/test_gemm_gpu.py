@@ -93,3 +93,31 @@ def test_gemm_rejects_bad_arguments():
     w = torch.randn(16, 60, device="cuda").bfloat16()
     with pytest.raises(RuntimeError):
         ops.gemm(x, w)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_grouped_wgrad_matches_separate_gemms(dtype, accumulate):
+    """ub200_gemm_grouped: the four weight-gradient shapes of a base layer in one launch."""
+    import ctypes as C
+    from uniter_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(3)
+    T, H, I = 1237, 768, 3072
+    probs = [(H, I), (I, H), (3 * H, H), (H, H)]           # (M, N) of dW2, dW1, dWqkv, dWo
+    args = (_lib.GemmArgs * 4)()
+    keep, refs, outs = [], [], []
+    for i, (M, N) in enumerate(probs):
+        a = (torch.randn(T, M, device="cuda") * 0.1).to(dtype)
+        b = torch.randn(T, N, device="cuda").to(dtype)
+        out = (torch.randn(M, N, device="cuda") * 0.5).to(dtype) if accumulate else \
+            torch.empty(M, N, device="cuda", dtype=dtype)
+        ref = a.float().t() @ b.float() + (out.float() if accumulate else 0)
+        keep += [a, b]; outs.append(out); refs.append(ref)
+        args[i] = _lib.GemmArgs(a=a.data_ptr(), b=b.data_ptr(), lda=M, ldb=N, a_major=1, b_major=1,
+                                M=M, N=N, K=T, dtype=_lib.dtype_code(dtype),
+                                epilogue=_lib.EPI_ACCUM if accumulate else 0, out=out.data_ptr(), ldo=N)
+    _lib.check(lib.ub200_gemm_grouped(args, 4, _lib.current_stream()))
+    torch.cuda.synchronize()
+    for out, ref in zip(outs, refs):
+        _close(out, ref, TOL[dtype], "grouped wgrad")

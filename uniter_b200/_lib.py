@@ -89,6 +89,8 @@ def load():
     lib.ub200_device_check.restype = C.c_int
     lib.ub200_gemm.restype = C.c_int
     lib.ub200_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+    lib.ub200_gemm_grouped.restype = C.c_int
+    lib.ub200_gemm_grouped.argtypes = [C.POINTER(GemmArgs), C.c_int32, C.c_void_p]
     for name in ("ub200_attn_fwd", "ub200_attn_bwd"):
         getattr(lib, name).restype = C.c_int
         getattr(lib, name).argtypes = [C.POINTER(AttnArgs), C.c_void_p]

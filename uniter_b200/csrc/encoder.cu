@@ -25,12 +25,14 @@ struct ActLayout {
 };
 
 struct BwdScratch {
-  int64_t bufA, bufB, bufC, g0, g1, dpre, dqkv, attn_ws, total;
+  int64_t bufA, bufB, bufC, bufD, bufE, g0, g1, dpre, dqkv, attn_ws, total;
   BwdScratch(int64_t T, int64_t H, int64_t I, int64_t attn_ws_bytes) {
     int64_t o = 0;
-    bufA = o; o += align256(T * H * 2);
-    bufB = o; o += align256(T * H * 2);
-    bufC = o; o += align256(T * H * 2);
+    bufA = o; o += align256(T * H * 2);   // ds2
+    bufB = o; o += align256(T * H * 2);   // dy2 (dropout-masked ds2)
+    bufC = o; o += align256(T * H * 2);   // da, then dctx
+    bufD = o; o += align256(T * H * 2);   // ds1
+    bufE = o; o += align256(T * H * 2);   // dy1 (dropout-masked ds1)
     g0 = o;   o += align256(T * H * 2);
     g1 = o;   o += align256(T * H * 2);
     dpre = o; o += align256(T * I * 2);
@@ -256,14 +258,6 @@ extern "C" int ub200_encoder_bwd(const ub200_encoder_desc* d, const ub200_layer_
       ProfTag _t(9);
       UB_TRY(ub200_gemm(&g, stream));
     }
-    // ---- dW2[H, I] = dY2^T f
-    g = gemm_base(d);
-    g.a = dy2; g.lda = H; g.a_major = 1; g.b = A + L.f; g.ldb = I; g.b_major = 1;
-    g.M = H; g.N = I; g.K = T; g.epilogue = acc; g.out = gr.dw2; g.ldo = I;
-    {
-      ProfTag _t(10);
-      UB_TRY(ub200_gemm(&g, stream));
-    }
     // ---- da = dPre W1 + ds2   (bufC)
     g = gemm_base(d);
     g.a = sc + S.dpre; g.lda = I; g.b = w.w1; g.ldb = H; g.b_major = 1; g.M = T; g.N = H; g.K = I;
@@ -272,19 +266,11 @@ extern "C" int ub200_encoder_bwd(const ub200_encoder_desc* d, const ub200_layer_
       ProfTag _t(11);
       UB_TRY(ub200_gemm(&g, stream));
     }
-    // ---- dW1[I, H] = dPre^T a
-    g = gemm_base(d);
-    g.a = sc + S.dpre; g.lda = I; g.a_major = 1; g.b = A + L.a; g.ldb = H; g.b_major = 1;
-    g.M = I; g.N = H; g.K = T; g.epilogue = acc; g.out = gr.dw1; g.ldo = H;
-    {
-      ProfTag _t(12);
-      UB_TRY(ub200_gemm(&g, stream));
-    }
 
-    // ---- a = LN(s1): ds1 (bufA), masked copy (bufB), dgamma/dbeta, dbo
+    // ---- a = LN(s1): ds1 (bufD), masked copy (bufE), dgamma/dbeta, dbo
     ln = ub200_ln_bwd_args{};
-    ln.dy = sc + S.bufC; ln.x = A + L.s1; ln.gamma = w.ln1_g; ln.dx = sc + S.bufA;
-    ln.dx_drop = drop ? sc + S.bufB : nullptr;
+    ln.dy = sc + S.bufC; ln.x = A + L.s1; ln.gamma = w.ln1_g; ln.dx = sc + S.bufD;
+    ln.dx_drop = drop ? sc + S.bufE : nullptr;
     ln.dgamma = gr.small + SG.dg1; ln.dbeta = gr.small + SG.db1ln; ln.dbias = gr.small + SG.dbo;
     ln.rows = T; ln.hidden = H; ln.dtype = d->dtype; ln.dropout_p = d->hidden_dropout_p;
     ln.rng_seed = d->rng_seed; ln.rng_stream = rng_stream_of(d, l, SITE_ATTN_OUT);
@@ -292,22 +278,14 @@ extern "C" int ub200_encoder_bwd(const ub200_encoder_desc* d, const ub200_layer_
       ProfTag _t(13);
       UB_TRY(ub200_layernorm_bwd(&ln, stream));
     }
-    const void* dy1 = drop ? sc + S.bufB : sc + S.bufA;
+    const void* dy1 = drop ? sc + S.bufE : sc + S.bufD;
 
-    // ---- dctx = dY1 Wo   (bufC)
+    // ---- dctx = dY1 Wo   (bufC; da is dead after the LayerNorm backward)
     g = gemm_base(d);
     g.a = dy1; g.lda = H; g.b = w.wo; g.ldb = H; g.b_major = 1; g.M = T; g.N = H; g.K = H;
     g.out = sc + S.bufC; g.ldo = H;
     {
       ProfTag _t(14);
-      UB_TRY(ub200_gemm(&g, stream));
-    }
-    // ---- dWo[H, H] = dY1^T ctx
-    g = gemm_base(d);
-    g.a = dy1; g.lda = H; g.a_major = 1; g.b = A + L.ctx; g.ldb = H; g.b_major = 1;
-    g.M = H; g.N = H; g.K = T; g.epilogue = acc; g.out = gr.dwo; g.ldo = H;
-    {
-      ProfTag _t(15);
       UB_TRY(ub200_gemm(&g, stream));
     }
 
@@ -332,18 +310,30 @@ extern "C" int ub200_encoder_bwd(const ub200_encoder_desc* d, const ub200_layer_
     // ---- dx = dqkv Wqkv + ds1  -> gradient wrt the layer input
     g = gemm_base(d);
     g.a = sc + S.dqkv; g.lda = 3 * H; g.b = w.wqkv; g.ldb = H; g.b_major = 1; g.M = T; g.N = H; g.K = 3 * H;
-    g.epilogue = UB200_EPI_RESIDUAL; g.residual = sc + S.bufA; g.ldr = H; g.out = dnext; g.ldo = H;
+    g.epilogue = UB200_EPI_RESIDUAL; g.residual = sc + S.bufD; g.ldr = H; g.out = dnext; g.ldo = H;
     {
       ProfTag _t(18);
       UB_TRY(ub200_gemm(&g, stream));
     }
-    // ---- dWqkv[3H, H] = dqkv^T x
-    g = gemm_base(d);
-    g.a = sc + S.dqkv; g.lda = 3 * H; g.a_major = 1; g.b = x; g.ldb = H; g.b_major = 1;
-    g.M = 3 * H; g.N = H; g.K = T; g.epilogue = acc; g.out = gr.dwqkv; g.ldo = H;
+
+    // ---- the four weight gradients of the layer as ONE grouped launch (all contract over T):
+    //      dW2[H,I] = dY2^T f ; dW1[I,H] = dPre^T a ; dWo[H,H] = dY1^T ctx ; dWqkv[3H,H] = dQKV^T x
     {
-      ProfTag _t(19);
-      UB_TRY(ub200_gemm(&g, stream));
+      ub200_gemm_args wg[4];
+      for (int i = 0; i < 4; ++i) {
+        wg[i] = gemm_base(d);
+        wg[i].a_major = 1; wg[i].b_major = 1; wg[i].K = T; wg[i].epilogue = acc;
+      }
+      wg[0].a = dy2; wg[0].lda = H; wg[0].b = A + L.f; wg[0].ldb = I;
+      wg[0].M = H; wg[0].N = I; wg[0].out = gr.dw2; wg[0].ldo = I;
+      wg[1].a = sc + S.dpre; wg[1].lda = I; wg[1].b = A + L.a; wg[1].ldb = H;
+      wg[1].M = I; wg[1].N = H; wg[1].out = gr.dw1; wg[1].ldo = H;
+      wg[2].a = sc + S.dqkv; wg[2].lda = 3 * H; wg[2].b = x; wg[2].ldb = H;
+      wg[2].M = 3 * H; wg[2].N = H; wg[2].out = gr.dwqkv; wg[2].ldo = H;
+      wg[3].a = dy1; wg[3].lda = H; wg[3].b = A + L.ctx; wg[3].ldb = H;
+      wg[3].M = H; wg[3].N = H; wg[3].out = gr.dwo; wg[3].ldo = H;
+      ProfTag _t(10);
+      UB_TRY(ub200_gemm_grouped(wg, 4, stream));
     }
 
     // gradient flowing into the previous layer's output (+ its external gradient, if any)

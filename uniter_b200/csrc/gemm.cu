@@ -9,6 +9,8 @@ int gemm_dispatch_bf16(int bn, int cluster, int a_major, int b_major, const Gemm
                        const CUtensorMap& tmA, const CUtensorMap& tmB, int grid, cudaStream_t stream);
 int gemm_dispatch_f16(int bn, int cluster, int a_major, int b_major, const GemmParams& p,
                       const CUtensorMap& tmA, const CUtensorMap& tmB, int grid, cudaStream_t stream);
+int gemm_group_dispatch_bf16(const void* tm, const GroupedParams& g, int grid, cudaStream_t stream);
+int gemm_group_dispatch_f16(const void* tm, const GroupedParams& g, int grid, cudaStream_t stream);
 
 // Pick (N tile, CTAs per tile) minimising  waves x k-blocks x cycles-per-k-block + exposed tail.
 // Cycles per k-block are MEASURED on B200 (K = 12288 sweep, mainloop only): they are far from
@@ -113,4 +115,38 @@ extern "C" int ub200_gemm(const ub200_gemm_args* args, ub200_stream_t stream_) {
   if (a.dtype == UB200_BF16)
     return gemm_dispatch_bf16(bn, cluster, a.a_major, a.b_major, p, tmA, tmB, grid, stream);
   return gemm_dispatch_f16(bn, cluster, a.a_major, a.b_major, p, tmA, tmB, grid, stream);
+}
+
+extern "C" int ub200_gemm_grouped(const ub200_gemm_args* args, int32_t count, ub200_stream_t stream_) {
+  using namespace ub;
+  UB_CHECK_ARG(args != nullptr && count >= 1 && count <= GEMM_MAX_GROUP,
+               "gemm_grouped: need 1..%d problems", GEMM_MAX_GROUP);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  struct { CUtensorMap a[GEMM_MAX_GROUP]; CUtensorMap b[GEMM_MAX_GROUP]; } tm;
+  GroupedParams g{};
+  g.nprob = count; g.K = args[0].K; g.epilogue = args[0].epilogue;
+  int tiles = 0;
+  for (int i = 0; i < count; ++i) {
+    const ub200_gemm_args& a = args[i];
+    UB_CHECK_ARG(a.a && a.b && a.out, "gemm_grouped[%d]: null operand", i);
+    UB_CHECK_ARG(a.a_major == 1 && a.b_major == 1, "gemm_grouped[%d]: operands must be MN-major (wgrad form)", i);
+    UB_CHECK_ARG(a.K == g.K && a.dtype == args[0].dtype && a.epilogue == g.epilogue,
+                 "gemm_grouped[%d]: K / dtype / epilogue must match problem 0", i);
+    UB_CHECK_ARG(a.M > 0 && a.N > 0 && a.K > 0 && a.N % 8 == 0 && a.ldo % 8 == 0,
+                 "gemm_grouped[%d]: bad shape", i);
+    int rc = make_tma_2d(&tm.a[i], a.a, a.dtype, a.K, a.M, a.lda, BK, 64);
+    if (rc) return rc;
+    rc = make_tma_2d(&tm.b[i], a.b, a.dtype, a.K, a.N, a.ldb, BK, 64);
+    if (rc) return rc;
+    g.M[i] = a.M; g.N[i] = a.N; g.out[i] = a.out; g.ldo[i] = a.ldo;
+    g.tiles_n[i] = (a.N + 127) / 128;
+    g.tile_start[i] = tiles;
+    tiles += ((a.M + BM - 1) / BM) * g.tiles_n[i];
+  }
+  for (int i = count; i <= GEMM_MAX_GROUP; ++i) g.tile_start[i] = tiles;
+  for (int i = count; i < GEMM_MAX_GROUP; ++i) { tm.a[i] = tm.a[0]; tm.b[i] = tm.b[0]; }
+  int grid = num_sms();
+  if (grid > tiles) grid = tiles;
+  if (args[0].dtype == UB200_BF16) return gemm_group_dispatch_bf16(&tm, g, grid, stream);
+  return gemm_group_dispatch_f16(&tm, g, grid, stream);
 }

@@ -427,6 +427,157 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
+// =================================================================================== grouped wgrad
+// The four weight-gradient GEMMs of a layer (dW2 = dY2^T f, dW1 = dPre^T a, dWo = dY1^T ctx,
+// dWqkv = dQKV^T x; all contract over K = T tokens, both operands MN-major) as ONE persistent
+// launch: 432 tiles of 128x128 on 148 SMs (2.9 balanced rounds) instead of four launches of
+// 144 / 144 / 36 / 108 tiles, each with its own prologue and exposed epilogue tail.
+struct TmPack {
+  CUtensorMap a[GEMM_MAX_GROUP];
+  CUtensorMap b[GEMM_MAX_GROUP];
+};
+
+__device__ __forceinline__ int group_of_tile(const GroupedParams& g, int tile) {
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < GEMM_MAX_GROUP; ++i)
+    if (i < g.nprob && tile >= g.tile_start[i]) pi = i;
+  return pi;
+}
+
+template <bool kBF16, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_group_kernel(const __grid_constant__ TmPack tm, const GroupedParams g) {
+  constexpr int BN = 128;
+  using Cfg = GemmCfg<BN, 1>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (g.K + BK - 1) / BK;
+  const int num_tiles = g.tile_start[g.nprob];
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int pi = group_of_tile(g, tile);
+        const int lt = tile - g.tile_start[pi];
+        const int m0 = (lt / g.tiles_n[pi]) * BM;
+        const int n0 = (lt % g.tiles_n[pi]) * BN;
+        const CUtensorMap* ta = &tm.a[pi];
+        const CUtensorMap* tb = &tm.b[pi];
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + A_TILE_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j)
+            tma_load_2d(sA + j * (64 * BK * 2), ta, &full_bar[stage], m0 + j * 64, kb * BK);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(sB + j * (64 * BK * 2), tb, &full_bar[stage], n0 + j * 64, kb * BK);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(kBF16 ? 1 : 0, 1, 1, BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sB = sA + A_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = umma_smem_desc(sA + k * 2048, 8192, 1024);
+            const uint64_t db = umma_smem_desc(sB + k * 2048, 8192, 1024);
+            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue (8 warps)
+    const int quarter = warp & 3;
+    const int chalf = (warp - 4) >> 2;
+    DropoutRng rng;
+    rng.k0 = rng.k1 = rng.s0 = rng.s1 = 0; rng.thr16 = 0; rng.inv_keep = 1.f;
+    float* epi_stage = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES) +
+                       (warp - 4) * (32 * 33);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int pi = group_of_tile(g, tile);
+      const int lt = tile - g.tile_start[pi];
+      const int m0 = (lt / g.tiles_n[pi]) * BM;
+      const int n0 = (lt % g.tiles_n[pi]) * BN;
+      GemmParams pp{};
+      pp.M = g.M[pi]; pp.N = g.N[pi]; pp.K = g.K; pp.epilogue = g.epilogue;
+      pp.out = g.out[pi]; pp.ldo = g.ldo[pi];
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + static_cast<uint32_t>(acc * BN) +
+                             (static_cast<uint32_t>(quarter * 32) << 16);
+      epilogue_warp<EPI, BN, kBF16>(pp, t_acc, m0 + quarter * 32, n0, chalf, lane, rng, epi_stage,
+                                    &tmem_empty_bar[acc], 0u, false);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
 // =================================================================================== 2-SM kernel
 // CTA pair (cluster of 2): output tile 256 x BN.  rank 0 = leader (issues the MMAs).
 template <int BN, bool A_MN, bool B_MN, bool kBF16, int EPI>
@@ -644,6 +795,24 @@ int gemm_dispatch(int bn, int cluster, int a_major, int b_major, const GemmParam
     case 256: return dispatch_major<256, kBF16, 1>(a_major, b_major, p, tmA, tmB, grid, stream);
   }
   return set_error(UB200_EINVAL, "gemm: tile_n must be 0, 64, 128, 192 or 256 (got %d)", bn);
+}
+
+template <bool kBF16>
+int gemm_group_dispatch(const TmPack& tm, const GroupedParams& g, int grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<128, 1>;
+  void (*kern)(const TmPack, const GroupedParams);
+  if (g.epilogue == 0) kern = gemm_group_kernel<kBF16, 0>;
+  else if (g.epilogue == UB200_EPI_ACCUM) kern = gemm_group_kernel<kBF16, UB200_EPI_ACCUM>;
+  else return set_error(UB200_EUNSUPPORTED, "gemm_grouped: epilogue must be 0 or ACCUM");
+  static bool configured[2] = {false, false};
+  const int ci = g.epilogue ? 1 : 0;
+  if (!configured[ci]) {
+    UB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured[ci] = true;
+  }
+  ProfScope ps(stream);
+  UB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, 1, tm, g));
+  return 0;
 }
 
 }  // namespace ub

@@ -23,4 +23,17 @@ struct GemmParams {
   int tiles_m, tiles_n;
 };
 
+
+// Grouped launch: up to 4 independent problems with the same K, operand majors (MN, MN) and
+// epilogue (the four weight-gradient GEMMs of one encoder layer) share one persistent grid.
+constexpr int GEMM_MAX_GROUP = 4;
+struct GroupedParams {
+  int nprob, K, epilogue;
+  int M[GEMM_MAX_GROUP], N[GEMM_MAX_GROUP];
+  void* out[GEMM_MAX_GROUP];
+  long long ldo[GEMM_MAX_GROUP];
+  int tiles_n[GEMM_MAX_GROUP];
+  int tile_start[GEMM_MAX_GROUP + 1];   // prefix sums of the per-problem tile counts
+};
+
 }  // namespace ub
