@@ -377,3 +377,75 @@ def test_chunked_backward_is_identical_to_single_call():
     for n, p in model.named_parameters():
         if n in g1 and n.startswith("encoder."):
             assert torch.equal(p.grad, g1[n]), n
+
+
+def _cfg(hidden, heads, inter, layers, vocab=2000, img_dim=2048, max_pos=512):
+    return dict(vocab_size=vocab, hidden_size=hidden, num_hidden_layers=layers, num_attention_heads=heads,
+                intermediate_size=inter, max_position_embeddings=max_pos, type_vocab_size=2, img_dim=img_dim)
+
+
+def test_large_geometry_forward_backward_vs_oracle():
+    """uniter-large geometry (config/uniter-large.json: H=1024, 16 heads, I=4096), 2 layers,
+    reduced vocabulary: forward + a few gradients against the CPU oracle."""
+    from uniter_b200.synth import synth_batch
+    cfg = _cfg(1024, 16, 4096, 2)
+    state = util.make_state(cfg, seed=5)
+    dtype = torch.float16
+    model = util.make_model(cfg, state, dtype).eval()
+    batch = synth_batch(8, 6, 20, 10, 60, seed=9, vocab_size=2000)
+    out = _fwd(model, batch, output_all_encoded_layers=False)
+    m = batch["attn_masks"].float().cuda()
+    scale = 256.0
+    ((((out.float() * m[..., None]) ** 2).sum() / m.sum() / out.size(-1)) * scale).backward()
+    rs = {k: v.to(dtype).float().requires_grad_(True) for k, v in state.items()}
+    ref = orc.uniter_forward(rs, 2, 16, batch["input_ids"], batch["position_ids"],
+                             batch["img_feat"].to(dtype).float(), batch["img_pos_feat"].to(dtype).float(),
+                             batch["attn_masks"], batch["gather_index"], output_all_encoded_layers=False)
+    v = _valid(batch)
+    _assert_close(out.float().cpu()[v], ref.detach()[v], dtype, "large geometry forward")
+    mc = batch["attn_masks"].float()
+    (((ref * mc[..., None]) ** 2).sum() / mc.sum() / ref.size(-1)).backward()
+    for name in ("encoder.layer.0.attention.self.value.weight", "encoder.layer.1.intermediate.dense.weight",
+                 "encoder.layer.0.output.dense.weight", "encoder.layer.1.attention.output.LayerNorm.weight",
+                 "encoder.layer.0.intermediate.dense.bias", "img_embeddings.img_linear.weight"):
+        got = dict(model.named_parameters())[name].grad.float().cpu() / scale
+        want = rs[name].grad
+        rel = ((got - want).norm() / (want.norm() + 1e-12)).item()
+        assert rel <= 3e-2, (name, rel)
+
+
+def test_full_size_c2_forward_vs_oracle_and_batch_invariance():
+    """BASELINE configs[1] at full size: UNITER-base 12 layers, B = 64, varlen (T = 3451).
+    (1) every valid row against the CPU fp32 oracle (weights rounded to fp16); (2) size-independent
+    property: a sample encoded alone equals its rows inside the batch (packing / varlen attention
+    never mixes sequences) — checked for the longest and the shortest sample."""
+    from uniter_b200.synth import synth_batch
+    cfg = _cfg(768, 12, 3072, 12, vocab=28996)
+    state = util.make_state(cfg, seed=2)
+    dtype = torch.float16
+    model = util.make_model(cfg, state, dtype).eval()
+    batch = synth_batch(64, 12, 28, 26, 46, 1234)
+    with torch.no_grad():
+        out = _fwd(model, batch, output_all_encoded_layers=False).float().cpu()
+    rs = util.rounded_state(state, dtype)
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    with torch.no_grad():
+        ref = orc.uniter_forward(rs, 12, 12, batch["input_ids"], batch["position_ids"],
+                                 batch["img_feat"].to(dtype).float(), batch["img_pos_feat"].to(dtype).float(),
+                                 batch["attn_masks"], batch["gather_index"], output_all_encoded_layers=False)
+    v = _valid(batch)
+    err = (out - ref)[v].abs()
+    assert err.max().item() <= 2e-2 and err.mean().item() <= 2e-3, (err.max().item(), err.mean().item())
+    lens = [a + b for a, b in zip(batch["txt_lens"], batch["num_bbs"])]
+    for k in (max(range(64), key=lambda i: lens[i]), min(range(64), key=lambda i: lens[i])):
+        tl, nb = batch["txt_lens"][k], batch["num_bbs"][k]
+        one = {
+            "input_ids": batch["input_ids"][k:k + 1, :tl], "position_ids": batch["position_ids"][:, :tl],
+            "img_feat": batch["img_feat"][k:k + 1, :nb], "img_pos_feat": batch["img_pos_feat"][k:k + 1, :nb],
+            "attn_masks": torch.ones(1, tl + nb, dtype=torch.long),
+            "gather_index": torch.arange(tl + nb).unsqueeze(0),
+        }
+        with torch.no_grad():
+            alone = _fwd(model, one, output_all_encoded_layers=False).float().cpu()
+        d = (alone[0] - out[k, :tl + nb]).abs().max().item()
+        assert d <= 1e-2, (k, d)
