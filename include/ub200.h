@@ -48,6 +48,12 @@ int ub200_device_check(void);                 /* 0 iff the current device is sm_
  * 12 FFN1 wgrad, 13 LN1 bwd, 14 attn-out dgrad, 15 attn-out wgrad, 16 attention bwd,
  * 17 dbias column sum, 18 QKV dgrad, 19 QKV wgrad, 20 gradient add. */
 unsigned long long ub200_launch_count(void);  /* kernels launched by this library so far */
+/* Persistent kernels of this library size their grids to the SM count.  While a collective (NCCL)
+ * runs concurrently on another stream its CTAs occupy SMs; a persistent CTA that cannot be placed
+ * starts a whole round late.  `n` SMs are left free by every later launch (0 restores the full
+ * device); returns the previous value.  Used by uniter_b200.distributed.GradientReducer while the
+ * chunked all-reduce overlaps the backward pass (replaces utils/distributed.py:16-43). */
+int ub200_set_sm_reserve(int n);
 int ub200_profile_enable(int on);
 int ub200_profile_collect(float* ms_per_tag, int* launches_per_tag, int ntags);
 

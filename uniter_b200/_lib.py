@@ -87,6 +87,8 @@ def load():
     lib.ub200_version.restype = C.c_int
     lib.ub200_last_error_string.restype = C.c_char_p
     lib.ub200_device_check.restype = C.c_int
+    lib.ub200_set_sm_reserve.restype = C.c_int
+    lib.ub200_set_sm_reserve.argtypes = [C.c_int]
     lib.ub200_gemm.restype = C.c_int
     lib.ub200_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
     lib.ub200_gemm_grouped.restype = C.c_int

@@ -17,6 +17,8 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+static int g_sm_reserve = 0;
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;
@@ -27,7 +29,15 @@ int num_sms() {
       n = 148;
     cached[dev] = n;
   }
-  return cached[dev];
+  int n = cached[dev] - g_sm_reserve;
+  n &= ~1;                 // CTA pairs (cta_group::2) need an even count
+  return n < 2 ? 2 : n;
+}
+
+int set_sm_reserve(int n) {
+  const int prev = g_sm_reserve;
+  g_sm_reserve = n < 0 ? 0 : n;
+  return prev;
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
@@ -96,6 +106,8 @@ ProfScope::~ProfScope() {
 extern "C" {
 
 unsigned long long ub200_launch_count(void) { return ub::g_launches; }
+
+int ub200_set_sm_reserve(int n) { return ub::set_sm_reserve(n); }
 
 int ub200_profile_enable(int on) {
   ub::g_prof_on = on != 0;

@@ -16,13 +16,26 @@ import torch.distributed as dist
 from .model import UniterModel
 
 
-def _avg_all_reduce(t, async_op=False):
+def _avg_all_reduce(t, async_op=False, group=None):
     """Mean over ranks.  NCCL reduces with AVG directly; gloo (CPU tests) sums then divides."""
     if dist.get_backend() == "nccl":
-        return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op)
+        return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op, group=group)
     w = dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=False)
     t.div_(dist.get_world_size())
     return None
+
+
+def _capped_nccl_group(max_ctas):
+    """A second NCCL communicator whose collectives use at most `max_ctas` CTAs, so that the
+    overlapped all-reduce and the persistent GEMM / row kernels (which leave exactly that many SMs
+    free, ub200_set_sm_reserve) do not fight over SMs.  None if this torch build cannot cap it."""
+    try:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.config.max_ctas = int(max_ctas)
+        opts.config.min_ctas = min(int(max_ctas), 4)
+        return dist.new_group(backend="nccl", pg_options=opts)
+    except Exception:     # older torch / NCCL without per-communicator config
+        return None
 
 
 def broadcast_parameters(model, root=0):
@@ -37,8 +50,19 @@ def broadcast_parameters(model, root=0):
 class GradientReducer:
     """Average gradients over ranks after backward: arena in place + one bucket for the rest."""
 
-    def __init__(self, model, overlap_chunks=4):
+    def __init__(self, model, overlap_chunks=4, sm_reserve=16):
+        """`overlap_chunks` > 1: the encoder arena is all-reduced in that many layer groups while
+        the backward of the earlier layers still runs.  `sm_reserve` > 0: during that overlap the
+        library's persistent kernels leave `sm_reserve` SMs to the collective, and the collective
+        runs on a communicator capped to the same number of CTAs (must be called by all ranks)."""
         self.model = model
+        self.sm_reserve = int(sm_reserve)
+        self._group = None
+        self._lib = None
+        if self.sm_reserve > 0 and overlap_chunks > 1 and dist.is_initialized() and dist.get_backend() == "nccl":
+            self._group = _capped_nccl_group(self.sm_reserve)
+            from . import _lib
+            self._lib = _lib.load()
         self.encoders = [m for m in model.modules() if isinstance(m, UniterModel)]
         self._others = None
         self._flat = None
@@ -46,6 +70,7 @@ class GradientReducer:
         self._pending = []
         self._reduced = set()
         self._comm_stream = None
+        self._reserved = False
 
     # ---- overlap: called by _EncoderStack.backward after the kernels of layers [lo, hi) are enqueued
     def _on_chunk(self, enc, lo, hi):
@@ -53,9 +78,12 @@ class GradientReducer:
             self._comm_stream = torch.cuda.Stream()
         ev = torch.cuda.Event()
         ev.record()
+        if self._lib is not None and not self._reserved:
+            self._lib.ub200_set_sm_reserve(self.sm_reserve)   # launches after this point
+            self._reserved = True
         with torch.cuda.stream(self._comm_stream):
             self._comm_stream.wait_event(ev)
-            self._pending.append(_avg_all_reduce(enc.arena_slice(lo, hi), async_op=True))
+            self._pending.append(_avg_all_reduce(enc.arena_slice(lo, hi), async_op=True, group=self._group))
         self._reduced.add(id(enc))
 
     def _arena_param_ids(self):
@@ -73,7 +101,7 @@ class GradientReducer:
         self._pending = []
         for enc in self.encoders:
             if id(enc) not in self._reduced:      # not already reduced chunk-wise during backward
-                works.append(_avg_all_reduce(enc.grad_arena(), async_op=True))
+                works.append(_avg_all_reduce(enc.grad_arena(), async_op=True, group=self._group))
         self._reduced = set()
         # parameters outside the arena (tied weights appear once: parameters() de-duplicates)
         others = [p for p in self.model.parameters() if p.grad is not None and id(p) not in arena_ids]
@@ -106,4 +134,7 @@ class GradientReducer:
         finally:
             for enc in self.encoders:
                 enc._bwd_chunk_hook = None
+            if self._reserved:
+                self._lib.ub200_set_sm_reserve(0)
+                self._reserved = False
         self.reduce()
