@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--overlap-chunks", type=int, default=4,
                     help="N>1: layer groups whose gradient all-reduce overlaps the backward pass")
-    ap.add_argument("--sm-reserve", type=int, default=16,
+    ap.add_argument("--sm-reserve", type=int, default=0,
                     help="N>1: SMs left to the overlapped all-reduce (and its CTA cap)")
     ap.add_argument("--layers", type=int, default=BASE["NL"], help=argparse.SUPPRESS)
     return ap.parse_args()
@@ -166,6 +166,12 @@ def cpu_reference_run(args, steps, warmup, sample_B):
 # =============================================================================== our arm
 def main():
     args = parse()
+    # exactly ONE line on stdout: libraries that print there (NCCL's version banner does) are
+    # diverted to stderr at the file-descriptor level; the JSON line goes to the saved descriptor
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
+    real_out = os.fdopen(out_fd, "w")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -185,7 +191,7 @@ def main():
                                  "kind": "port", "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_out, flush=True)
         return
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
@@ -398,7 +404,7 @@ def main():
             "achieved_tflops": round(flops_step / (ms_step * 1e-3) / 1e12, 1),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "breakdown": breakdown,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
