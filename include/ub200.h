@@ -80,6 +80,8 @@ int ub200_profile_collect(float* ms_per_tag, int* launches_per_tag, int ntags);
  *   UB200_EPI_ACCUM     v += out[m,n]   (previous contents, e.g. gradient accumulation)
  *   UB200_EPI_OUT_F32   out is fp32 instead of the 16-bit dtype
  *   UB200_EPI_COLSUM    colsum[n] += sum_m v  (fp32 atomics; bias gradients)
+ *   UB200_EPI_ATOMIC    out[m,n] += v with fp32 atomics (requires OUT_F32 and a pre-zeroed out);
+ *                       the only epilogue allowed with k_splits > 1 (split-K partial sums)
  * ------------------------------------------------------------------------------------------ */
 enum {
   UB200_EPI_BIAS = 1,
@@ -90,6 +92,7 @@ enum {
   UB200_EPI_ACCUM = 32,
   UB200_EPI_OUT_F32 = 64,
   UB200_EPI_COLSUM = 128,
+  UB200_EPI_ATOMIC = 256,
 };
 
 typedef struct {
@@ -114,6 +117,13 @@ typedef struct {
   int32_t max_ctas;        /* 0 = one CTA per SM */
   int32_t cluster;         /* 0 = heuristic, 1 = single CTAs, 2 = 2-CTA clusters sharing B by
                               TMA multicast */
+  int32_t k_splits;        /* 0 / 1 = none; n > 1: K is cut into <= n slices that run as independent
+                              work units (few output tiles, long K: the MLM decoder's dgrad) and meet
+                              through UB200_EPI_ATOMIC; -1 = as many as fill the SMs */
+  int32_t n_valid;         /* 0 = N; else B only holds n_valid of the N output features (rows if
+                              b_major == 0, columns if b_major == 1): the rest contribute acc = 0.
+                              Lets N be padded to a multiple of 8 over an unpadded weight (the tied
+                              decoder [28996, H] of model/layer.py:206-222) */
 } ub200_gemm_args;
 
 int ub200_gemm(const ub200_gemm_args* args, ub200_stream_t stream);
@@ -181,7 +191,8 @@ typedef struct {
   const int32_t* row_kind;  /* optional [rows]: only rows with row_kind[r] == kind are processed
                                (the embedding front-end has different LayerNorms per row kind) */
   int32_t kind;
-  int32_t dropout_on_dy;    /* 1: y = dropout(LN(x)) (embeddings): mask dy instead of emitting dx_drop */
+  int32_t dropout_on_dy;    /* bit 0: y = dropout(LN(x)) (embeddings): mask dy instead of emitting dx_drop;
+                               bit 1: with row_kind, rows of the OTHER kind get dx = 0 (else untouched) */
 } ub200_ln_bwd_args;
 int ub200_layernorm_bwd(const ub200_ln_bwd_args* args, ub200_stream_t stream);
 
@@ -191,6 +202,11 @@ int ub200_colsum(const void* x, float* out, int32_t rows, int32_t cols, int64_t 
                  ub200_stream_t stream);
 int ub200_cvt_from_f32(const float* src, void* dst, int64_t n, int32_t accumulate, int32_t dtype,
                        ub200_stream_t stream);
+/* nseg segments of n elements: dst[s*dst_stride + j] (+)= 16-bit(src[s*src_stride + j]) — the small
+ * (bias / LayerNorm) gradients of several encoder layers finalised in one launch. */
+int ub200_cvt_from_f32_strided(const float* src, void* dst, int64_t n, int64_t nseg,
+                               int64_t src_stride, int64_t dst_stride, int32_t accumulate,
+                               int32_t dtype, ub200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Whole encoder stack: NL x BertLayer forward / backward in ONE call each, so that the host
@@ -302,6 +318,80 @@ typedef struct {
   uint64_t rng_seed, rng_stream;
 } ub200_embed_rows_args;
 int ub200_embed_rows_fwd(const ub200_embed_rows_args* args, ub200_stream_t stream);
+
+
+/* Backward of the embedding front-end's table lookups (autograd mirror of model/model.py:235-237,
+ * :258, :316-317), after ub200_layernorm_bwd produced du (gradient wrt the pre-LayerNorm sums) and
+ * dP (gradient wrt the pos_linear output, zero on text rows):
+ *   ub200_embed_bwd_scatter   text rows: d_word[word_id[t]] += du[t] (16-bit packed atomics into the
+ *                             pre-zeroed [V, H] gradient), d_pos[pos_id[t]] += du[t] (fp32)
+ *   ub200_embed_bwd_colsums   mode 0: d_type[ty, :] += sum_{t: type_id[t]==ty} x[t, :]     ([Ty, H] fp32)
+ *                             mode 1: d_wpos[h, k] += sum_{image rows t} x[t, h] * box[t, k] ([H, 7] fp32,
+ *                                     box = pos_feat[img_src[t]] rounded to the 16-bit dtype)
+ * fp32 outputs are accumulated (caller zeroes them). */
+int ub200_embed_bwd_scatter(const void* du, const int32_t* kind, const int32_t* word_id,
+                            const int32_t* pos_id, void* d_word, float* d_pos, int32_t T,
+                            int32_t hidden, int32_t dtype, ub200_stream_t stream);
+typedef struct {
+  const void* x;             /* [T, hidden] 16-bit: du (mode 0) or dP (mode 1) */
+  const int32_t* type_id;    /* mode 0 */
+  const int32_t* kind;       /* mode 1 */
+  const int32_t* img_src;    /* mode 1 */
+  const float* pos_feat;     /* mode 1: [B*Li, 7] fp32 */
+  float* out;                /* mode 0: [type_vocab, hidden]; mode 1: [hidden, 7] */
+  int32_t T, hidden, mode, type_vocab, dtype;
+} ub200_embed_colsum_args;
+int ub200_embed_bwd_colsums(const ub200_embed_colsum_args* args, ub200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Callers either side of the encoder.
+ *
+ * MLM head (model/layer.py:188-222 BertPredictionHeadTransform + tied decoder, model/pretrain.py:
+ * 107-127): dense+GELU, LayerNorm and the decoder run on ub200_gemm / ub200_layernorm_*; these
+ * are the pieces in between.  `logits` is [rows, ld] 16-bit with ld >= vocab rounded up to 8.
+ *   ub200_ce_fwd   loss[r] = logsumexp(logits[r, :vocab]) - logits[r, target[r]], lse[r] saved
+ *                  (F.cross_entropy(..., reduction='none'); targets outside [0, vocab) -> 0)
+ *   ub200_ce_bwd   dlogits[r, c] = (softmax - onehot) * dloss[r] for c < vocab, 0 for
+ *                  vocab <= c < ncols; dlogits may alias logits
+ *   ub200_dgelu_mul  out = dy * gelu_erf'(pre)   (n elements, n % 8 == 0)
+ * ------------------------------------------------------------------------------------------ */
+int ub200_ce_fwd(const void* logits, int64_t ld, const int64_t* targets, float* loss, float* lse,
+                 int32_t rows, int32_t vocab, int32_t dtype, ub200_stream_t stream);
+int ub200_ce_bwd(const void* logits, void* dlogits, int64_t ld, const int64_t* targets,
+                 const float* lse, const float* dloss, int32_t rows, int32_t vocab, int32_t ncols,
+                 int32_t dtype, ub200_stream_t stream);
+int ub200_dgelu_mul(const void* dy, const void* pre, void* out, int64_t n, int32_t dtype,
+                    ub200_stream_t stream);
+
+/* Multi-tensor AdamW on fp32 master weights: replaces optim/adamw.py:43-103 (+ the apex O2
+ * master-gradient copy, unscale and master->model copy around it, train_vqa.py:152,190-227) and
+ * torch.nn.utils.clip_grad_norm_ (train_vqa.py:223-226).  One segment per parameter tensor;
+ * `segs` and `blk_start` (int32 [nseg + 1], prefix sums of ceil(n / ub200_adam_chunk())) live in
+ * DEVICE memory, nblocks = blk_start[nseg].  Per element, with g = grad * inv_scale * clip:
+ *   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= step_size * m / (sqrt(v) + eps) ;
+ *   p -= lr_wd * p  (lr * weight_decay, AFTER the Adam update) ; model = round16(p)
+ * step_size = lr * sqrt(1 - b2^t) / (1 - b1^t) (or lr without bias correction) is computed by
+ * the caller per segment.  clip = min(1, max_norm / (sqrt(sumsq) * inv_scale + 1e-6)) is read
+ * from the device scalar written by ub200_grad_sumsq (no host synchronisation). */
+typedef struct {
+  const void* grad;       /* [n] gradient in grad_dtype */
+  float* master;          /* [n] fp32 master weights */
+  float* exp_avg;         /* [n] fp32 */
+  float* exp_avg_sq;      /* [n] fp32 */
+  void* model;            /* [n] model weights in model_dtype, or NULL */
+  int64_t n;
+  float step_size;
+  float lr_wd;
+  int32_t grad_dtype;     /* UB200_F16 / UB200_BF16 / UB200_F32 */
+  int32_t model_dtype;
+} ub200_adam_segment;
+enum { UB200_F32 = 2 };
+int32_t ub200_adam_chunk(void);
+int ub200_grad_sumsq(const ub200_adam_segment* segs_dev, const int32_t* blk_start_dev, int32_t nseg,
+                     int32_t nblocks, float* out, ub200_stream_t stream);
+int ub200_adamw_step(const ub200_adam_segment* segs_dev, const int32_t* blk_start_dev, int32_t nseg,
+                     int32_t nblocks, float beta1, float beta2, float eps, float inv_scale,
+                     float max_norm, const float* sumsq, ub200_stream_t stream);
 
 #ifdef __cplusplus
 }

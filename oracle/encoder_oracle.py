@@ -176,6 +176,48 @@ def mlm_forward(state, num_layers, num_heads, batch):
     return torch.nn.functional.cross_entropy(scores, batch["txt_labels"][mask], reduction="none")
 
 
+def vqa_head(state, pooled, prefix="vqa_output."):
+    """model/vqa.py:23-28,44 — Linear(H, 2H) -> GELU -> LayerNorm(2H) -> Linear(2H, answers)."""
+    h = gelu_erf(linear(pooled, state[prefix + "0.weight"], state[prefix + "0.bias"]))
+    h = layer_norm(h, state[prefix + "2.weight"], state[prefix + "2.bias"])
+    return linear(h, state[prefix + "3.weight"], state[prefix + "3.bias"])
+
+
+def itm_head(state, pooled, prefix="itm_output."):
+    """model/pretrain.py:163-164 / model/itm.py:20 — Linear(H, 2) on the pooled output."""
+    return linear(pooled, state[prefix + "weight"], state[prefix + "bias"])
+
+
+# ----------------------------------------------------------------------------- optimizer
+def clip_grad_norm(grads, max_norm):
+    """torch.nn.utils.clip_grad_norm_ as called at train_vqa.py:223-226: total 2-norm over all
+    gradients; coef = max_norm / (total + 1e-6); gradients are scaled only if coef < 1.
+    Returns (clipped grads, total_norm)."""
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).float()
+    coef = max_norm / (total + 1e-6)
+    if coef < 1:
+        grads = [g * coef for g in grads]
+    return grads, total
+
+
+def adamw_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-6, weight_decay=0.0,
+               correct_bias=True):
+    """optim/adamw.py:62-101, one parameter tensor, fp32: returns (p, m, v) after step `step`
+    (1-based).  m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; denom = sqrt(v) + eps;
+    step_size = lr * sqrt(1-b2^t) / (1-b1^t); p -= step_size * m / denom; then the decoupled
+    decay p -= lr * wd * p on the UPDATED p (:99-100)."""
+    m = m * beta1 + (1.0 - beta1) * g
+    v = v * beta2 + (1.0 - beta2) * g * g
+    denom = v.sqrt() + eps
+    step_size = lr
+    if correct_bias:
+        step_size = step_size * math.sqrt(1.0 - beta2 ** step) / (1.0 - beta1 ** step)
+    p = p - step_size * (m / denom)
+    if weight_decay > 0.0:
+        p = p - lr * weight_decay * p
+    return p, m, v
+
+
 # ----------------------------------------------------------------------------- host-side index logic
 def get_gather_index(txt_lens, num_bbs, batch_size, max_len, out_size):
     """data/data.py:271-279 — canonical compaction index (pure integer logic)."""

@@ -168,6 +168,126 @@ def run_heads(rm, rvqa, rpre, out_path):
     print("wrote", out_path, "%.1f KB" % (os.path.getsize(out_path) / 1024))
 
 
+def import_reference_data():
+    """data/sampler.py, data/vqa.py, data/mlm.py import horovod / lmdb / lz4 / msgpack / (cy)toolz
+    at module level; none of them is used by the sampler or the collate functions except
+    cytoolz.partition_all and toolz.sandbox.unzip, shimmed here with their documented behaviour."""
+    def shim(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    def partition_all(n, seq):
+        seq = list(seq)
+        for i in range(0, len(seq), n):
+            yield tuple(seq[i:i + n])
+
+    def unzip(seq):
+        return tuple(zip(*list(seq)))
+
+    hv = shim("horovod")
+    hv.torch = shim("horovod.torch", rank=lambda: 0, size=lambda: 1)
+    shim("cytoolz", partition_all=partition_all, concat=lambda x: [b for a in x for b in a], curry=lambda f: f)
+    tz = shim("toolz")
+    tz.sandbox = shim("toolz.sandbox", unzip=unzip)
+    shim("lmdb")
+    l4 = shim("lz4")
+    l4.frame = shim("lz4.frame", compress=None, decompress=None)
+    shim("msgpack")
+    shim("msgpack_numpy", patch=lambda: None)
+    shim("tqdm", tqdm=lambda x, **k: x)
+    sys.path.insert(0, REF)
+    import data.sampler as rsamp
+    import data.vqa as rvqa_data
+    import data.mlm as rmlm_data
+    return rsamp, rvqa_data, rmlm_data
+
+
+def batching_samples(seed, n, with_labels):
+    """Per-sample tensors as the reference datasets' __getitem__ return them (data/vqa.py:30-42,
+    data/mlm.py:62-94), seeded."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        tl = int(torch.randint(3, 12, (1,), generator=g))
+        nbb = int(torch.randint(2, 9, (1,), generator=g))
+        ids = torch.randint(1000, 2000, (tl,), generator=g)
+        feat = torch.randn(nbb, 16, generator=g)
+        pos = torch.rand(nbb, 7, generator=g)
+        am = torch.ones(tl + nbb, dtype=torch.long)
+        if with_labels:
+            lab = torch.full((tl,), -1, dtype=torch.long)
+            m = torch.rand(tl, generator=g) < 0.3
+            lab[m] = ids[m]
+            out.append((ids, feat, pos, am, lab))
+        else:
+            out.append((ids, feat, pos, am, torch.rand(5, generator=g)))
+    return out
+
+
+def run_batching(out_path):
+    """The reference's own TokenBucketSampler and collate functions on seeded inputs."""
+    import random
+    rsamp, rvqa_data, rmlm_data = import_reference_data()
+    rec = {}
+    g = torch.Generator().manual_seed(17)
+    lens = torch.randint(10, 120, (500,), generator=g).tolist()
+    rec["lens"] = np.array(lens)
+    random.seed(5)
+    batches = list(iter(rsamp.TokenBucketSampler(lens, bucket_size=128, batch_size=1024, droplast=False)))
+    rec["batches_flat"] = np.array([i for b in batches for i in b])
+    rec["batches_len"] = np.array([len(b) for b in batches])
+    random.seed(6)
+    batches = list(iter(rsamp.TokenBucketSampler(lens, bucket_size=64, batch_size=800, droplast=True,
+                                                 size_multiple=4)))
+    rec["batches2_flat"] = np.array([i for b in batches for i in b])
+    rec["batches2_len"] = np.array([len(b) for b in batches])
+    for name, fn, lab in (("vqa", rvqa_data.vqa_collate, False), ("mlm", rmlm_data.mlm_collate, True)):
+        b = fn(batching_samples(31, 6, lab))
+        for k, v in b.items():
+            rec["%s/%s" % (name, k)] = v.numpy()
+    np.savez_compressed(out_path, **rec)
+    print("wrote", out_path, "%.1f KB" % (os.path.getsize(out_path) / 1024))
+
+
+def run_adamw(out_path):
+    """4 steps of the reference's own AdamW (optim/adamw.py) + clip_grad_norm_ on seeded fp32
+    tensors: two param groups (decay 0.01 / 0), a linear-warmup lr per step, gradient clipping at
+    2.0 (train_vqa.py:223-226 default --grad_norm 2.0)."""
+    import warnings
+    sys.path.insert(0, REF)
+    from optim.adamw import AdamW
+    g = torch.Generator().manual_seed(21)
+    shapes = [(37, 16), (16,), (5, 8, 3), (129,)]
+    params = [torch.nn.Parameter(torch.randn(s, generator=g) * 0.1) for s in shapes]
+    opt = AdamW([{"params": [params[0], params[2]], "weight_decay": 0.01},
+                 {"params": [params[1], params[3]], "weight_decay": 0.0}],
+                lr=3e-4, betas=(0.9, 0.98))
+    rec = {"n_params": np.array(len(shapes)), "betas": np.array([0.9, 0.98]), "eps": np.array(1e-6),
+           "weight_decay": np.array([0.01, 0.0, 0.01, 0.0]), "max_norm": np.array(2.0)}
+    for i, p in enumerate(params):
+        rec["p0_%d" % i] = p.detach().numpy().copy()
+    lrs = [1e-4, 2e-4, 3e-4, 2.5e-4]
+    rec["lrs"] = np.array(lrs)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for t, lr in enumerate(lrs):
+            for grp in opt.param_groups:
+                grp["lr"] = lr
+            for i, p in enumerate(params):
+                scale = 30.0 if t == 1 else 1.0        # step 1 exceeds the clip threshold
+                p.grad = torch.randn(p.shape, generator=g) * 0.05 * scale
+                rec["g%d_%d" % (t, i)] = p.grad.numpy().copy()
+            total = torch.nn.utils.clip_grad_norm_(params, 2.0)
+            rec["norm%d" % t] = np.array(float(total))
+            opt.step()
+            for i, p in enumerate(params):
+                rec["p%d_%d" % (t + 1, i)] = p.detach().numpy().copy()
+    np.savez_compressed(out_path, **rec)
+    print("wrote", out_path, "%.1f KB" % (os.path.getsize(out_path) / 1024))
+
+
 TINY = dict(vocab_size_or_config_json_file=2000, hidden_size=128, num_hidden_layers=2,
             num_attention_heads=2, intermediate_size=512, hidden_act="gelu",
             hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1,
@@ -195,6 +315,8 @@ def main():
     c1b = synth_batch(2, 0, 0, 0, 0, seed=0, txt_lens=[20, 14], num_bbs=[36, 30])
     run_case(rm, BASE_L1, 2048, c1b, os.path.join(HERE, "c1b.npz"), full_grads=False)
     run_heads(rm, rvqa, rpre, os.path.join(HERE, "heads_tiny.npz"))
+    run_adamw(os.path.join(HERE, "adamw.npz"))
+    run_batching(os.path.join(HERE, "batching.npz"))
 
 
 if __name__ == "__main__":

@@ -121,3 +121,51 @@ def test_grouped_wgrad_matches_separate_gemms(dtype, accumulate):
     torch.cuda.synchronize()
     for out, ref in zip(outs, refs):
         _close(out, ref, TOL[dtype], "grouped wgrad")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape,splits", [((190, 768, 28996), -1), ((190, 768, 28996), 7), ((64, 128, 1000), 3),
+                                          ((300, 256, 200), 16), ((130, 64, 64), -1)])
+def test_gemm_split_k_atomic(dtype, shape, splits):
+    """Few output tiles, long K (the MLM decoder's dgrad, K = vocabulary): K slices run as
+    independent work units and meet through fp32 atomics; K tails are zero-filled by TMA."""
+    from uniter_b200 import ops
+    M, N, K = shape
+    torch.manual_seed(M + K)
+    Kp = (K + 7) // 8 * 8
+    x = torch.zeros(M, Kp, device="cuda", dtype=dtype)[:, :K]
+    x.copy_((torch.randn(M, K, device="cuda") * 0.05).to(dtype))
+    wt = (torch.randn(K, N, device="cuda") * 0.05).to(dtype)          # [K, N]: dgrad form
+    ref = x.float() @ wt.float()
+    out = ops.gemm(x, wt, b_major=1, k_splits=splits)
+    assert out.dtype == torch.float32
+    _close(out, ref, 2e-3, "split-K dgrad form")
+    w = wt.t().contiguous()
+    wp = torch.zeros(N, Kp, device="cuda", dtype=dtype)[:, :K]
+    wp.copy_(w)
+    _close(ops.gemm(x, wp, k_splits=splits), ref, 2e-3, "split-K K-major")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,V,K", [(190, 28996, 768), (5, 1001, 128), (300, 2004, 128)])
+def test_gemm_n_valid_over_unpadded_weight(dtype, M, V, K):
+    """N padded to a multiple of 8 over a weight that only has V rows (tied decoder [28996, H]):
+    the padding columns see acc = 0 (+ bias), nothing past the weight is read into valid columns."""
+    from uniter_b200 import ops
+    torch.manual_seed(V)
+    Vp = (V + 7) // 8 * 8
+    x = torch.randn(M, K, device="cuda").to(dtype)
+    w = (torch.randn(V, K, device="cuda") * 0.05).to(dtype)
+    bias = torch.full((Vp,), -30000.0, device="cuda", dtype=dtype)
+    bias[:V] = torch.randn(V, device="cuda").to(dtype)
+    out = torch.empty(M, Vp, device="cuda", dtype=dtype)
+    ops.gemm(x, w, bias=bias, out=out, n_valid=V)
+    ref = x.float() @ w.float().t() + bias[:V].float()
+    _close(out[:, :V], ref, TOL[dtype], "n_valid forward")
+    if Vp != V:
+        assert (out[:, V:].float() == -30000.0).all()
+    # wgrad over the same padded buffer: A = out[:, :V] read MN-major with row pitch Vp
+    z = torch.randn(M, K, device="cuda").to(dtype)
+    d = (torch.randn(M, Vp, device="cuda") * 0.1).to(dtype)
+    dv = d[:, :V]
+    _close(ops.gemm(dv, z, a_major=1, b_major=1), dv.float().t() @ z.float(), TOL[dtype], "wgrad M = V")

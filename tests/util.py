@@ -63,3 +63,39 @@ def batch_to(batch, device):
 def rounded_state(state, dtype):
     """fp32 copy of the weights pre-rounded to the kernel dtype (oracle side of a parity check)."""
     return {k: v.to(dtype).float() for k, v in state.items()}
+
+
+def head_state(module, seed, ties=()):
+    """Seeded weights for one of our head modules, reproducing what the reference module holds
+    after `load_state_dict(seeded_state(reference.state_dict() schema, seed))` in
+    tests/golden/make_goldens.py: every key is drawn independently (sha1(key) ^ seed), and a
+    parameter that the reference ties under a second name ends up with the value of the key that
+    is loaded LAST — `ties` lists (our key, reference alias loaded later)."""
+    from uniter_b200.synth import seeded_state
+    shapes = {k: tuple(v.shape) for k, v in module.state_dict().items()}
+    for ours, alias in ties:
+        shapes[alias] = shapes[ours]
+    st = seeded_state(shapes, seed=seed)
+    for ours, alias in ties:
+        st[ours] = st.pop(alias)
+    return st
+
+
+PRETRAIN_TIES = (("uniter.embeddings.word_embeddings.weight", "cls.predictions.decoder.weight"),
+                 ("uniter.img_embeddings.img_linear.weight", "feat_regress.weight"))
+
+
+def heads_batch():
+    from uniter_b200.synth import synth_batch
+    return synth_batch(3, 5, 9, 4, 8, seed=7, img_dim=64, vocab_size=2000, mlm_prob=0.3)
+
+
+def tiny_config():
+    from uniter_b200.model import UniterConfig
+    c = TINY
+    return UniterConfig(c["vocab_size"], hidden_size=c["hidden_size"],
+                        num_hidden_layers=c["num_hidden_layers"],
+                        num_attention_heads=c["num_attention_heads"],
+                        intermediate_size=c["intermediate_size"],
+                        max_position_embeddings=c["max_position_embeddings"],
+                        type_vocab_size=c["type_vocab_size"])

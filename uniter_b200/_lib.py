@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libub200.so")
 F16, BF16 = 0, 1
 EPI_BIAS, EPI_DROPOUT, EPI_RESIDUAL, EPI_GELU = 1, 2, 4, 8
 EPI_DGELU, EPI_ACCUM, EPI_OUT_F32, EPI_COLSUM = 16, 32, 64, 128
+EPI_ATOMIC = 256
 
 
 class GemmArgs(C.Structure):
@@ -27,6 +28,7 @@ class GemmArgs(C.Structure):
         ("dropout_p", C.c_float),
         ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64),
         ("tile_n", C.c_int32), ("max_ctas", C.c_int32), ("cluster", C.c_int32),
+        ("k_splits", C.c_int32), ("n_valid", C.c_int32),
     ]
 
 
@@ -71,6 +73,21 @@ class EmbedRowsArgs(C.Structure):
         ("dropout_p", C.c_float), ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64)]
 
 
+class EmbedColsumArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("type_id", C.c_void_p), ("kind", C.c_void_p),
+                ("img_src", C.c_void_p), ("pos_feat", C.c_void_p), ("out", C.c_void_p),
+                ("T", C.c_int32), ("hidden", C.c_int32), ("mode", C.c_int32),
+                ("type_vocab", C.c_int32), ("dtype", C.c_int32)]
+
+
+class AdamSegment(C.Structure):
+    _fields_ = [("grad", C.c_void_p), ("master", C.c_void_p), ("exp_avg", C.c_void_p),
+                ("exp_avg_sq", C.c_void_p), ("model", C.c_void_p), ("n", C.c_int64),
+                ("step_size", C.c_float), ("lr_wd", C.c_float),
+                ("grad_dtype", C.c_int32), ("model_dtype", C.c_int32)]
+
+
+F32 = 2
 _lib = None
 
 
@@ -113,6 +130,32 @@ def load():
                                             C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.ub200_embed_rows_fwd.restype = C.c_int
     lib.ub200_embed_rows_fwd.argtypes = [C.POINTER(EmbedRowsArgs), C.c_void_p]
+    lib.ub200_embed_bwd_scatter.restype = C.c_int
+    lib.ub200_embed_bwd_scatter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.ub200_embed_bwd_colsums.restype = C.c_int
+    lib.ub200_embed_bwd_colsums.argtypes = [C.POINTER(EmbedColsumArgs), C.c_void_p]
+    lib.ub200_cvt_from_f32_strided.restype = C.c_int
+    lib.ub200_cvt_from_f32_strided.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                               C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+    lib.ub200_ce_fwd.restype = C.c_int
+    lib.ub200_ce_fwd.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                 C.c_int32, C.c_int32, C.c_void_p]
+    lib.ub200_ce_bwd.restype = C.c_int
+    lib.ub200_ce_bwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.ub200_dgelu_mul.restype = C.c_int
+    lib.ub200_dgelu_mul.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    lib.ub200_cvt_from_f32.restype = C.c_int
+    lib.ub200_cvt_from_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+    lib.ub200_adam_chunk.restype = C.c_int32
+    lib.ub200_grad_sumsq.restype = C.c_int
+    lib.ub200_grad_sumsq.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.ub200_adamw_step.restype = C.c_int
+    lib.ub200_adamw_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float,
+                                     C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    lib.ub200_gather_rows.restype = C.c_int
+    lib.ub200_gather_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     _lib = lib
     return lib
 
@@ -122,12 +165,14 @@ def check(rc):
         raise RuntimeError("libub200 error %d: %s" % (rc, load().ub200_last_error_string().decode()))
 
 
-def dtype_code(t):
+def dtype_code(t, allow_f32=False):
     import torch
     if t == torch.bfloat16:
         return BF16
     if t == torch.float16:
         return F16
+    if t == torch.float32 and allow_f32:
+        return F32
     raise TypeError("libub200 computes in fp16 or bf16, got %s" % t)
 
 

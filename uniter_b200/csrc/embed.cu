@@ -291,6 +291,129 @@ embed_rows_fwd_kernel(const RowsParams p) {
   }
 }
 
+
+// ------------------------------------------------------------------------------ backward: tables
+// Gradient of the three embedding-table lookups of a TEXT row (model/model.py:235-237):
+//   d_word[word_id[t]] += du[t]   16-bit packed atomics into the pre-zeroed [V, H] gradient
+//                                 (what torch's index_add_ does in the model dtype)
+//   d_pos [pos_id[t]]  += du[t]   fp32 atomics ([P, H] staging, converted once afterwards)
+// One warp per packed row, 16-byte loads; image rows return immediately.
+template <bool kBF16>
+__global__ void __launch_bounds__(256)
+embed_bwd_scatter_kernel(const void* __restrict__ du_, const int* __restrict__ kind,
+                         const int* __restrict__ word_id, const int* __restrict__ pos_id,
+                         void* __restrict__ d_word_, float* __restrict__ d_pos, int T, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
+  using T16 = typename Elem<kBF16>::T;
+  using T16x2 = typename Elem<kBF16>::T2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (t >= T || kind[t] != 0) return;
+  const int nvec = H >> 3;
+  const uint4* du = reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(du_) + static_cast<size_t>(t) * H);
+  T16* wrow = reinterpret_cast<T16*>(d_word_) + static_cast<size_t>(word_id[t]) * H;
+  float* prow = d_pos + static_cast<size_t>(pos_id[t]) * H;
+  for (int v = lane; v < nvec; v += 32) {
+    const uint4 u = __ldg(du + v);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      T16x2 pr;
+      *reinterpret_cast<uint32_t*>(&pr) = w[q];
+      atomicAdd(reinterpret_cast<T16x2*>(wrow + v * 8 + q * 2), pr);
+      const float2 f = Elem<kBF16>::unpack(w[q]);
+      atomicAdd(prow + v * 8 + q * 2, f.x);
+      atomicAdd(prow + v * 8 + q * 2 + 1, f.y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ weighted column sums
+//   out[k * stride_k + n * stride_n] += sum_t w_k(t) * x[t, n],   k < W
+// mode 0  w_k(t) = (type_id[t] - base == k)               -> token_type table gradient [Ty, H]
+// mode 1  w_k(t) = 16-bit(pos_feat[img_src[t], k]), k < 7 -> pos_linear.weight gradient [H, 7]
+//                  (image rows only: the K = 7 wgrad of model/model.py:258 as a reduction)
+// CTA = 32 column vectors (256 columns) x 8 row lanes over a slab of rows; per-thread fp32
+// accumulators, one smem reduction and one atomic per (k, column) per CTA.
+struct WColsumParams {
+  const void* x;            // [T, N] 16-bit
+  const int* type_id;       // mode 0
+  const int* kind;          // mode 1
+  const int* img_src;       // mode 1
+  const float* pos_feat;    // mode 1: [*, 7] fp32
+  float* out;
+  int T, N, mode, base, nweights, rows_per_cta;
+  long long stride_k, stride_n;
+};
+
+template <bool kBF16>
+__global__ void __launch_bounds__(256)
+wcolsum_kernel(const WColsumParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  using T16 = typename Elem<kBF16>::T;
+  constexpr int W = 8;
+  __shared__ float red[8][256 + 1];
+  const int cv = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col0 = (blockIdx.x * 32 + cv) * 8;
+  const int r0 = blockIdx.y * p.rows_per_cta;
+  const int r1 = min(p.T, r0 + p.rows_per_cta);
+  float acc[W][8];
+#pragma unroll
+  for (int k = 0; k < W; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
+  if (col0 < p.N) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      float w[W];
+#pragma unroll
+      for (int k = 0; k < W; ++k) w[k] = 0.f;
+      bool any = false;
+      if (p.mode == 0) {
+        const int ty = p.type_id[r] - p.base;
+        if (ty >= 0 && ty < W) {
+          any = true;
+#pragma unroll
+          for (int k = 0; k < W; ++k) w[k] = (ty == k) ? 1.f : 0.f;
+        }
+      } else {
+        const int s = p.img_src[r];
+        if (p.kind[r] == 1 && s >= 0) {
+          any = true;
+          const float* box = p.pos_feat + static_cast<size_t>(s) * 7;
+#pragma unroll
+          for (int k = 0; k < 7; ++k) w[k] = Elem<kBF16>::to_f(Elem<kBF16>::from_f(__ldg(box + k)));
+        }
+      }
+      if (!any) continue;
+      float f[8];
+      e_unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(p.x) +
+                                                            static_cast<size_t>(r) * p.N + col0)), f);
+#pragma unroll
+      for (int k = 0; k < W; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[k][e] = fmaf(w[k], f[e], acc[k][e]);
+    }
+  }
+  const int c = threadIdx.x;
+  const int col = blockIdx.x * 256 + c;
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    if (k >= p.nweights) break;     // uniform
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[rl][cv * 8 + e] = acc[k][e];
+    __syncthreads();
+    if (col < p.N) {
+      float s = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) s += red[w8][c];
+      if (s != 0.f) atomicAdd(p.out + k * p.stride_k + col * p.stride_n, s);
+    }
+  }
+}
+
 }  // namespace ub
 
 // ------------------------------------------------------------------------------ C ABI
@@ -388,5 +511,54 @@ extern "C" int ub200_embed_rows_fwd(const ub200_embed_rows_args* a, ub200_stream
   }
 #undef UB_LAUNCH
   UB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ub200_embed_bwd_scatter(const void* du, const int32_t* kind, const int32_t* word_id,
+                                       const int32_t* pos_id, void* d_word, float* d_pos, int32_t T,
+                                       int32_t hidden, int32_t dtype, ub200_stream_t stream_) {
+  using namespace ub;
+  UB_CHECK_ARG(du && kind && word_id && pos_id && d_word && d_pos, "embed_bwd_scatter: null pointer");
+  UB_CHECK_ARG(T > 0 && hidden > 0 && hidden % 8 == 0, "embed_bwd_scatter: need T > 0, hidden %% 8 == 0");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int grid = (T + 7) / 8;
+  ProfScope ps(stream);
+  if (dtype == UB200_BF16)
+    UB_CHECK_CUDA(launch_pdl(embed_bwd_scatter_kernel<true>, dim3(grid), dim3(256), 0, stream, 1, du, kind,
+                             word_id, pos_id, d_word, d_pos, T, hidden));
+  else
+    UB_CHECK_CUDA(launch_pdl(embed_bwd_scatter_kernel<false>, dim3(grid), dim3(256), 0, stream, 1, du, kind,
+                             word_id, pos_id, d_word, d_pos, T, hidden));
+  return 0;
+}
+
+extern "C" int ub200_embed_bwd_colsums(const ub200_embed_colsum_args* a, ub200_stream_t stream_) {
+  using namespace ub;
+  UB_CHECK_ARG(a && a->x && a->out, "embed_bwd_colsums: null pointer");
+  UB_CHECK_ARG(a->T > 0 && a->hidden > 0 && a->hidden % 8 == 0, "embed_bwd_colsums: need T > 0, hidden %% 8 == 0");
+  UB_CHECK_ARG(a->mode == 0 || a->mode == 1, "embed_bwd_colsums: bad mode %d", a->mode);
+  UB_CHECK_ARG(a->mode != 0 || (a->type_id && a->type_vocab > 0), "embed_bwd_colsums: mode 0 needs type_id / type_vocab");
+  UB_CHECK_ARG(a->mode != 1 || (a->kind && a->img_src && a->pos_feat), "embed_bwd_colsums: mode 1 needs kind / img_src / pos_feat");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  WColsumParams p{};
+  p.x = a->x; p.type_id = a->type_id; p.kind = a->kind; p.img_src = a->img_src; p.pos_feat = a->pos_feat;
+  p.out = a->out; p.T = a->T; p.N = a->hidden; p.mode = a->mode;
+  const int gx = (a->hidden + 255) / 256;
+  int gy = 32;                                   // few row slabs: W x hidden atomics per slab
+  if (gy > (a->T + 63) / 64) gy = (a->T + 63) / 64;
+  if (gy < 1) gy = 1;
+  p.rows_per_cta = (a->T + gy - 1) / gy;
+  const int total = a->mode == 0 ? a->type_vocab : 7;
+  for (int base = 0; base < total; base += 8) {
+    p.base = base;
+    p.nweights = total - base < 8 ? total - base : 8;
+    if (a->mode == 0) { p.stride_k = a->hidden; p.stride_n = 1; p.out = a->out + static_cast<long long>(base) * a->hidden; }
+    else { p.stride_k = 1; p.stride_n = 7; }
+    ProfScope ps(stream);
+    if (a->dtype == UB200_BF16)
+      UB_CHECK_CUDA(launch_pdl(wcolsum_kernel<true>, dim3(gx, gy), dim3(256), 0, stream, 1, p));
+    else
+      UB_CHECK_CUDA(launch_pdl(wcolsum_kernel<false>, dim3(gx, gy), dim3(256), 0, stream, 1, p));
+  }
   return 0;
 }

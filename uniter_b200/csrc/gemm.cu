@@ -59,6 +59,13 @@ extern "C" int ub200_gemm(const ub200_gemm_args* args, ub200_stream_t stream_) {
   UB_CHECK_ARG(!((epi & UB200_EPI_GELU) && (epi & UB200_EPI_OUT_F32)),
                "gemm: EPI_GELU with fp32 output is not supported");
   UB_CHECK_ARG(a.dropout_p >= 0.f && a.dropout_p < 1.f, "gemm: dropout_p out of range");
+  UB_CHECK_ARG(!(epi & UB200_EPI_ATOMIC) || epi == (UB200_EPI_ATOMIC | UB200_EPI_OUT_F32),
+               "gemm: EPI_ATOMIC combines with EPI_OUT_F32 only");
+  UB_CHECK_ARG(a.k_splits >= -1, "gemm: k_splits must be >= -1");
+  UB_CHECK_ARG(a.k_splits == 0 || a.k_splits == 1 || (epi & UB200_EPI_ATOMIC),
+               "gemm: k_splits > 1 needs EPI_ATOMIC | EPI_OUT_F32 and a zeroed output");
+  UB_CHECK_ARG(a.n_valid >= 0 && a.n_valid <= a.N, "gemm: n_valid must be in [0, N]");
+  const int n_valid = a.n_valid ? a.n_valid : a.N;
 
   const int sms = num_sms();
   int bn = 0, cluster = 0;
@@ -68,6 +75,11 @@ extern "C" int ub200_gemm(const ub200_gemm_args* args, ub200_stream_t stream_) {
     if (!a.cluster) cluster = ((bn == 128 || bn == 256) && a.M > BM) ? 2 : 1;
   }
   if (a.cluster) cluster = a.cluster;
+  const bool splitk = a.k_splits > 1 || a.k_splits == -1;
+  if (splitk) {              // split-K units live in the 1-SM kernel
+    cluster = 1;
+    if (!a.tile_n) bn = a.N >= 128 ? 128 : 64;
+  }
   UB_CHECK_ARG(cluster == 1 || cluster == 2, "gemm: cluster must be 0, 1 or 2 (got %d)", cluster);
   UB_CHECK_ARG(!(cluster == 2 && (bn == 64 || bn == 192)), "gemm: cluster 2 needs tile_n 128 or 256");
 
@@ -79,9 +91,9 @@ extern "C" int ub200_gemm(const ub200_gemm_args* args, ub200_stream_t stream_) {
     rc = make_tma_2d(&tmA, a.a, a.dtype, a.K, a.M, a.lda, BK, 64);
   if (rc) return rc;
   if (a.b_major == 0)  // in 2-SM mode each CTA stages half of the B rows
-    rc = make_tma_2d(&tmB, a.b, a.dtype, a.N, a.K, a.ldb, bn / cluster, BK);
+    rc = make_tma_2d(&tmB, a.b, a.dtype, n_valid, a.K, a.ldb, bn / cluster, BK);
   else
-    rc = make_tma_2d(&tmB, a.b, a.dtype, a.K, a.N, a.ldb, BK, 64);
+    rc = make_tma_2d(&tmB, a.b, a.dtype, a.K, n_valid, a.ldb, BK, 64);
   if (rc) return rc;
 
   GemmParams p;
@@ -106,7 +118,18 @@ extern "C" int ub200_gemm(const ub200_gemm_args* args, ub200_stream_t stream_) {
   p.stream_hi = static_cast<uint32_t>(a.rng_stream >> 32);
   p.tiles_m = (a.M + BM - 1) / BM;
   p.tiles_n = (a.N + bn - 1) / bn;
-  const int units = ((p.tiles_m + cluster - 1) / cluster) * p.tiles_n;
+  const int num_kb = (a.K + BK - 1) / BK;
+  p.ksplit = 1;
+  p.kb_per_split = num_kb;
+  if (splitk) {
+    const int tiles = p.tiles_m * p.tiles_n;
+    int want = a.k_splits == -1 ? (sms + tiles - 1) / tiles : a.k_splits;
+    if (want > num_kb) want = num_kb;
+    if (want < 1) want = 1;
+    p.kb_per_split = (num_kb + want - 1) / want;
+    p.ksplit = (num_kb + p.kb_per_split - 1) / p.kb_per_split;   // every slice has >= 1 k-block
+  }
+  const int units = ((p.tiles_m + cluster - 1) / cluster) * p.tiles_n * p.ksplit;
   int slots = (a.max_ctas > 0 ? a.max_ctas : sms) / cluster;
   if (slots < 1) slots = 1;
   if (slots > units) slots = units;

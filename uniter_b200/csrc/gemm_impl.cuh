@@ -225,8 +225,13 @@ __device__ __forceinline__ void epilogue_warp(const GemmParams& p, uint32_t t_ac
           v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w;
           v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
         }
-        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        if (E.has(UB200_EPI_ATOMIC)) {     // split-K partial sums meet in a pre-zeroed fp32 output
+#pragma unroll
+          for (int i = 0; i < 8; ++i) atomicAdd(o + i, v[i]);
+        } else {
+          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
       } else {
         if (E.has(UB200_EPI_ACCUM)) {
           float t[8];
@@ -295,6 +300,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.K + BK - 1) / BK;
   const int num_tiles = p.tiles_m * p.tiles_n;
+  // work unit = (tile, k-slice): unit % num_tiles is the tile, unit / num_tiles the slice of
+  // kb_per_split k-blocks (ksplit == 1: one slice covering all of K)
+  const int num_units = num_tiles * p.ksplit;
   if (threadIdx.x == 0) UB_TRACE(0);
 
   if (warp == 0 && lane == 0) {
@@ -329,10 +337,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int tile = unit % num_tiles;
+        const int kb0 = (unit / num_tiles) * p.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + p.kb_per_split);
         const int m0 = (tile / p.tiles_n) * BM;
         const int n0 = (tile % p.tiles_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + A_TILE_BYTES;
@@ -352,7 +363,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_2d(sB + j * (64 * BK * 2), &tmB, &full_bar[stage], n0 + j * 64, kb * BK);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
-          if (kb == 0 && tile == blockIdx.x) UB_TRACE(2);
+          if (kb == kb0 && unit == static_cast<int>(blockIdx.x)) UB_TRACE(2);
         }
       }
       UB_TRACE(3);
@@ -369,21 +380,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int kb0 = (unit / num_tiles) * p.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + p.kb_per_split);
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (kb == 0 && tile == blockIdx.x) UB_TRACE(4);
+          if (kb == kb0 && unit == static_cast<int>(blockIdx.x)) UB_TRACE(4);
           const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sB = sA + A_TILE_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = umma_smem_desc(sA + k * A_KSTEP, A_LBO, 1024);
             const uint64_t db = umma_smem_desc(sB + k * B_KSTEP, B_LBO, 1024);
-            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_ss(d_tmem, da, db, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -402,17 +415,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                        (warp - 4) * (32 * 33);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int tile = unit % num_tiles;
       const int m0 = (tile / p.tiles_n) * BM;
       const int n0 = (tile % p.tiles_n) * BN;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      if (warp == 4 && lane == 0) UB_TRACE(tile == blockIdx.x ? 6 : 8);
+      if (warp == 4 && lane == 0) UB_TRACE(unit == static_cast<int>(blockIdx.x) ? 6 : 8);
       const uint32_t t_acc = tmem_base + static_cast<uint32_t>(acc * BN) +
                              (static_cast<uint32_t>(quarter * 32) << 16);
       epilogue_warp<EPI, BN, kBF16>(p, t_acc, m0 + quarter * 32, n0, chalf, lane, rng, epi_stage,
                                     &tmem_empty_bar[acc], 0u, false);
-      if (warp == 4 && lane == 0) UB_TRACE(tile == blockIdx.x ? 7 : 9);
+      if (warp == 4 && lane == 0) UB_TRACE(unit == static_cast<int>(blockIdx.x) ? 7 : 9);
       if (warp == 11 && lane == 0) UB_TRACE(10);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

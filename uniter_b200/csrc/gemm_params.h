@@ -21,6 +21,8 @@ struct GemmParams {
   float drop_inv_keep;
   uint32_t seed_lo, seed_hi, stream_lo, stream_hi;
   int tiles_m, tiles_n;
+  int ksplit;          // >= 1: work unit = (tile, k-slice); > 1 needs the fp32 atomic epilogue
+  int kb_per_split;    // k-blocks per slice
 };
 
 

@@ -106,6 +106,7 @@ struct LnBwdParams {
   const int* row_kind;  // optional [rows]: only rows with row_kind[row] == kind take part
   int kind;
   int dy_drop;          // 1: the dropout mask applies to dy (y = dropout(LN(x)), embeddings)
+  int zero_inactive;    // 1: rows of the other kind get dx = 0 (instead of being left untouched)
 };
 
 // NV = vectors (8 columns) per lane = ceil(H / 256): register arrays are sized for the actual
@@ -189,7 +190,15 @@ ln_bwd_kernel(const LnBwdParams p) {
         }
       }
     }
-    if (!active) continue;           // row belongs to the other LayerNorm (embedding front-end)
+    if (!active) {                   // row belongs to the other LayerNorm (embedding front-end)
+      if (p.zero_inactive) {
+        uint4* zr = reinterpret_cast<uint4*>(reinterpret_cast<T16*>(p.dx) + static_cast<size_t>(row) * H);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (lane + i * 32 < nvec) zr[lane + i * 32] = make_uint4(0, 0, 0, 0);
+      }
+      continue;
+    }
     const float mean = warp_sum(sum) * inv_h;
     float sq = 0.f;
 #pragma unroll
@@ -330,16 +339,20 @@ colsum_kernel(const void* __restrict__ x_, float* __restrict__ out, int rows, in
 // ------------------------------------------------------------------------------ fp32 -> 16-bit
 template <bool kBF16>
 __global__ void __launch_bounds__(256)
-cvt_kernel(const float* __restrict__ src, void* __restrict__ dst_, long long n, int accumulate) {
+cvt_kernel(const float* __restrict__ src, void* __restrict__ dst_, long long n, long long nseg,
+           long long src_stride, long long dst_stride, int accumulate) {
   pdl_launch_dependents();
   pdl_wait();
   using T16 = typename Elem<kBF16>::T;
   T16* dst = reinterpret_cast<T16*>(dst_);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+  const long long total = n * nseg;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float v = src[i];
-    if (accumulate) v += Elem<kBF16>::to_f(dst[i]);
-    dst[i] = Elem<kBF16>::from_f(v);
+    const long long seg = i / n, j = i - seg * n;
+    float v = src[seg * src_stride + j];
+    T16* d = dst + seg * dst_stride + j;
+    if (accumulate) v += Elem<kBF16>::to_f(*d);
+    *d = Elem<kBF16>::from_f(v);
   }
 }
 
@@ -426,17 +439,17 @@ int launch_colsum(int dtype, const void* x, float* out, int rows, int N, int ld,
   return 0;
 }
 
-int launch_cvt(int dtype, const float* src, void* dst, long long n, int accumulate,
-               cudaStream_t stream) {
-  if (n <= 0) return 0;
-  long long blocks = (n + 255) / 256;
+int launch_cvt(int dtype, const float* src, void* dst, long long n, long long nseg,
+               long long src_stride, long long dst_stride, int accumulate, cudaStream_t stream) {
+  if (n <= 0 || nseg <= 0) return 0;
+  long long blocks = (n * nseg + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 8;
   if (blocks > cap) blocks = cap;
   ProfScope ps(stream);
   if (dtype == UB200_BF16)
-    UB_CHECK_CUDA(launch_pdl(cvt_kernel<true>, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, 1, src, dst, n, accumulate));
+    UB_CHECK_CUDA(launch_pdl(cvt_kernel<true>, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, 1, src, dst, n, nseg, src_stride, dst_stride, accumulate));
   else
-    UB_CHECK_CUDA(launch_pdl(cvt_kernel<false>, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, 1, src, dst, n, accumulate));
+    UB_CHECK_CUDA(launch_pdl(cvt_kernel<false>, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, 1, src, dst, n, nseg, src_stride, dst_stride, accumulate));
   UB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -480,13 +493,14 @@ extern "C" int ub200_layernorm_bwd(const ub200_ln_bwd_args* a, ub200_stream_t st
   p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.dbias = a->dbias;
   p.rows = a->rows; p.H = a->hidden;
   p.row_kind = a->row_kind; p.kind = a->kind; p.dy_drop = 0;
+  p.zero_inactive = (a->dropout_on_dy & 2) ? 1 : 0;
   if (a->dropout_p > 0.f) {
-    UB_CHECK_ARG(a->dx_drop || a->dropout_on_dy, "layernorm_bwd: dropout_p > 0 needs dx_drop");
+    UB_CHECK_ARG(a->dx_drop || (a->dropout_on_dy & 1), "layernorm_bwd: dropout_p > 0 needs dx_drop");
     uint32_t thr = static_cast<uint32_t>(a->dropout_p * 65536.0f + 0.5f);
     if (thr > 65535u) thr = 65535u;
     if (thr == 0u) thr = 1u;
-    p.dx_drop = a->dropout_on_dy ? nullptr : a->dx_drop;
-    p.dy_drop = a->dropout_on_dy ? 1 : 0;
+    p.dx_drop = (a->dropout_on_dy & 1) ? nullptr : a->dx_drop;
+    p.dy_drop = (a->dropout_on_dy & 1) ? 1 : 0;
     p.drop_thr16 = thr;
     p.drop_inv_keep = 65536.0f / static_cast<float>(65536u - thr);
   } else {
@@ -515,5 +529,14 @@ extern "C" int ub200_colsum(const void* x, float* out, int32_t rows, int32_t col
 extern "C" int ub200_cvt_from_f32(const float* src, void* dst, int64_t n, int32_t accumulate,
                                   int32_t dtype, ub200_stream_t stream) {
   UB_CHECK_ARG(src && dst, "cvt_from_f32: null pointer");
-  return ub::launch_cvt(dtype, src, dst, n, accumulate, reinterpret_cast<cudaStream_t>(stream));
+  return ub::launch_cvt(dtype, src, dst, n, 1, 0, 0, accumulate, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ub200_cvt_from_f32_strided(const float* src, void* dst, int64_t n, int64_t nseg,
+                                          int64_t src_stride, int64_t dst_stride, int32_t accumulate,
+                                          int32_t dtype, ub200_stream_t stream) {
+  UB_CHECK_ARG(src && dst, "cvt_from_f32_strided: null pointer");
+  UB_CHECK_ARG(n >= 0 && nseg >= 0, "cvt_from_f32_strided: negative size");
+  return ub::launch_cvt(dtype, src, dst, n, nseg, src_stride, dst_stride, accumulate,
+                        reinterpret_cast<cudaStream_t>(stream));
 }

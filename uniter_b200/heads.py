@@ -1,16 +1,34 @@
-"""Callers of the hot path used by the benchmark / smoke configs: the MLM pre-training head.
+"""Callers of the hot path: the reference's task heads on top of the drop-in `UniterModel`.
 
-The reference's heads are out of scope to rewrite: they are kept as plain
-torch modules here with the reference's parameter names so a `UniterForPretraining` checkpoint
-loads (`uniter.*`, `cls.predictions.*`), and they consume the drop-in `UniterModel` exactly as
-model/pretrain.py:107-133 does (text slice -> masked rows only -> transform -> tied decoder).
-Kernels for this head are row (f)-1 of SURVEY.md §8 ("next").
+Parameter names and module trees follow the reference so its checkpoints load
+(`uniter.*`, `cls.predictions.*`, `vqa_output.*`, `itm_output.*`, `rank_output.*`):
+
+* ``UniterForMLM`` — the MLM branch of ``UniterForPretraining`` (model/pretrain.py:50-60,
+  107-133).  SURVEY.md §8f-1: the head runs on libub200 — masked rows are gathered straight from
+  the PACKED encoder output, ``BertPredictionHeadTransform`` (model/layer.py:188-203) is the
+  tcgen05 GEMM with the bias+GELU epilogue + the LayerNorm kernel, the tied decoder
+  (model/layer.py:206-222) is the same GEMM over the un-padded [V, H] embedding table
+  (``n_valid``), and the cross-entropy is one fused kernel per direction; the decoder's dgrad
+  (few output tiles, K = V = 28996) runs split-K.
+* ``UniterForVisualQuestionAnswering`` (model/vqa.py:16-52) and ``UniterForImageTextRetrieval``
+  (model/itm.py:14-59): pooler + small classifier, plain torch on top of the encoder — they are
+  here so the parity tests can check head-level logits against the reference's goldens.
 """
+from collections import defaultdict
+
 import torch
 from torch import nn
 from torch.nn import functional as F
 
-from .model import UniterModel, UniterPreTrainedModel
+from . import ops
+from .model import UniterModel, UniterPreTrainedModel, gather_packed_rows
+
+
+class GELU(nn.Module):
+    """model/layer.py:40-42 (erf form)."""
+
+    def forward(self, x):
+        return F.gelu(x)
 
 
 def gelu(x):
@@ -18,15 +36,12 @@ def gelu(x):
 
 
 class BertPredictionHeadTransform(nn.Module):
-    """model/layer.py:188-203."""
+    """model/layer.py:188-203 (parameter container; the fused head reads the weights by pointer)."""
 
     def __init__(self, config):
         super().__init__()
         self.dense = nn.Linear(config.hidden_size, config.hidden_size)
         self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=1e-12)
-
-    def forward(self, hidden_states):
-        return self.LayerNorm(gelu(self.dense(hidden_states)))
 
 
 class BertLMPredictionHead(nn.Module):
@@ -40,17 +55,64 @@ class BertLMPredictionHead(nn.Module):
         self.decoder.weight = bert_model_embedding_weights
         self.bias = nn.Parameter(torch.zeros(bert_model_embedding_weights.size(0)))
 
-    def forward(self, hidden_states):
-        return self.decoder(self.transform(hidden_states)) + self.bias
-
 
 class BertOnlyMLMHead(nn.Module):
     def __init__(self, config, bert_model_embedding_weights):
         super().__init__()
         self.predictions = BertLMPredictionHead(config, bert_model_embedding_weights)
 
-    def forward(self, sequence_output):
-        return self.predictions(sequence_output)
+
+_PAD_LOGIT = -30000.0   # finite in fp16 and bf16; exp(pad - max) underflows to exactly 0
+
+
+class _MlmHead(torch.autograd.Function):
+    """scores = decoder(LayerNorm(gelu(dense(h)))) + bias ; loss = cross_entropy(scores, targets)
+    on libub200.  Returns the per-row loss (fp32) or, with ``want_scores``, the [n, V] scores."""
+
+    @staticmethod
+    def forward(ctx, h, dense_w, dense_b, ln_g, ln_b, word_w, dec_bias, targets, want_scores):
+        n, H = h.shape
+        V = word_w.size(0)
+        Vp = (V + 7) // 8 * 8
+        dtype = h.dtype
+        t, pre = ops.gemm(h, dense_w, bias=dense_b, gelu=True)        # model/layer.py:199-200
+        z = ops.layernorm_fwd(t, ln_g, ln_b)                         # :201
+        if Vp != V:
+            bias_p = torch.full((Vp,), _PAD_LOGIT, device=h.device, dtype=dtype)
+            bias_p[:V] = dec_bias
+        else:
+            bias_p = dec_bias
+        logits = torch.empty(n, Vp, device=h.device, dtype=dtype)
+        ops.gemm(z, word_w, bias=bias_p, out=logits, n_valid=V if Vp != V else 0)   # :220-221
+        if want_scores:           # validation path (compute_loss=False): forward only
+            scores = logits[:, :V]
+            ctx.mark_non_differentiable(scores)
+            return scores
+        targets = targets.contiguous()
+        loss, lse = ops.ce_fwd(logits, targets, V)                    # model/pretrain.py:122-125
+        ctx.save_for_backward(h, pre, t, z, logits, lse, targets, dense_w, ln_g, word_w)
+        ctx.V = V
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        h, pre, t, z, logits, lse, targets, dense_w, ln_g, word_w = ctx.saved_tensors
+        V = ctx.V
+        dtype = h.dtype
+        # the scores are dead after this point: the gradient overwrites them
+        dlog = ops.ce_bwd_(logits, targets, lse, dloss.contiguous().float(), V)
+        d_dec_bias = ops.cvt_from_f32(ops.colsum(dlog)[:V], dtype)
+        dlv = dlog[:, :V]                                             # [n, V], row pitch Vp
+        # dz = dlog W_dec: 2 x (H / 128) output tiles, K = V -> split-K over the SMs (fp32 atomics)
+        dz = ops.cvt_from_f32(ops.gemm(dlv, word_w, b_major=1, k_splits=-1), dtype)
+        d_word = ops.gemm(dlv, z, a_major=1, b_major=1)               # [V, H] = dlog^T z
+        dt, _, dg, db, _ = ops.layernorm_bwd(dz, t, ln_g, want_dbias=False)
+        dpre = ops.dgelu_mul(dt, pre)
+        dh = ops.gemm(dpre, dense_w, b_major=1)
+        d_dense_w = ops.gemm(dpre, h, a_major=1, b_major=1)
+        d_dense_b = ops.cvt_from_f32(ops.colsum(dpre), dtype)
+        return (dh, d_dense_w, d_dense_b, ops.cvt_from_f32(dg, dtype), ops.cvt_from_f32(db, dtype),
+                d_word, d_dec_bias, None, None)
 
 
 class UniterForMLM(UniterPreTrainedModel):
@@ -63,23 +125,89 @@ class UniterForMLM(UniterPreTrainedModel):
         self.apply(self.init_weights)
 
     def forward(self, batch, compute_loss=True):
+        batch = defaultdict(lambda: None, batch)
         input_ids = batch["input_ids"]
-        txt_labels = batch["txt_labels"]
-        sequence_output = self.uniter(input_ids, batch["position_ids"], batch["img_feat"],
-                                      batch["img_pos_feat"], batch["attn_masks"],
-                                      batch["gather_index"], output_all_encoded_layers=False)
-        if "mlm_index" in batch:
-            # loader-provided flat positions of the masked tokens: static-shape gather, no sync
-            H = sequence_output.size(-1)
-            masked_output = sequence_output.reshape(-1, H).index_select(0, batch["mlm_index"])
-            targets = batch["mlm_targets"]
+        packed, meta = self.uniter.encode_packed(
+            input_ids, batch["position_ids"], batch["img_feat"], batch["img_pos_feat"],
+            batch["attn_masks"], batch["gather_index"], output_all_encoded_layers=False,
+            txt_type_ids=batch["txt_type_ids"])
+        L = meta["L"]
+        if batch["mlm_index"] is not None:
+            # loader-provided flat positions (b * L + j) of the masked tokens: static shapes, no sync
+            flat, targets = batch["mlm_index"], batch["mlm_targets"]
         else:
-            sequence_output = sequence_output[:, :input_ids.size(1), :]
-            mask = (txt_labels != -1)
-            masked_output = sequence_output[mask.unsqueeze(-1).expand_as(sequence_output)] \
-                .contiguous().view(-1, sequence_output.size(-1))
-            targets = txt_labels[mask]
-        prediction_scores = self.cls(masked_output)
+            # model/pretrain.py:115-118,129-133: text part only, rows where txt_labels != -1
+            txt_labels = batch["txt_labels"]
+            pos = (txt_labels != -1).nonzero(as_tuple=False)           # device sync, like the reference
+            flat = pos[:, 0] * L + pos[:, 1]
+            targets = txt_labels[pos[:, 0], pos[:, 1]]
+        if flat.numel() == 0:
+            V = self.uniter.config.vocab_size
+            return packed.new_zeros(0, dtype=torch.float32) if compute_loss else packed.new_zeros(0, V)
+        rows = meta["unpack_idx"][flat]                                # packed row of each masked token
+        masked_output = gather_packed_rows(packed, rows)               # [n, H]
+        p = self.cls.predictions
+        return _MlmHead.apply(masked_output, p.transform.dense.weight, p.transform.dense.bias,
+                              p.transform.LayerNorm.weight, p.transform.LayerNorm.bias,
+                              p.decoder.weight, p.bias, targets, not compute_loss)
+
+
+class UniterForVisualQuestionAnswering(UniterPreTrainedModel):
+    """model/vqa.py:16-52."""
+
+    def __init__(self, config, img_dim, num_answer):
+        super().__init__(config)
+        self.uniter = UniterModel(config, img_dim)
+        self.vqa_output = nn.Sequential(
+            nn.Linear(config.hidden_size, config.hidden_size * 2),
+            GELU(),
+            nn.LayerNorm(config.hidden_size * 2, eps=1e-12),
+            nn.Linear(config.hidden_size * 2, num_answer))
+        self.apply(self.init_weights)
+
+    def forward(self, batch, compute_loss=True):
+        batch = defaultdict(lambda: None, batch)
+        sequence_output = self.uniter(batch["input_ids"], batch["position_ids"], batch["img_feat"],
+                                      batch["img_pos_feat"], batch["attn_masks"], batch["gather_index"],
+                                      output_all_encoded_layers=False)
+        pooled_output = self.uniter.pooler(sequence_output)
+        answer_scores = self.vqa_output(pooled_output)
         if compute_loss:
-            return F.cross_entropy(prediction_scores.float(), targets, reduction="none")
-        return prediction_scores
+            return F.binary_cross_entropy_with_logits(answer_scores, batch["targets"], reduction="none")
+        return answer_scores
+
+
+class UniterForImageTextRetrieval(UniterPreTrainedModel):
+    """model/itm.py:14-59 (ITM classifier of model/pretrain.py:159-176 shares ``itm_output``)."""
+
+    def __init__(self, config, img_dim, margin=0.2):
+        super().__init__(config)
+        self.uniter = UniterModel(config, img_dim)
+        self.itm_output = nn.Linear(config.hidden_size, 2)
+        self.rank_output = nn.Linear(config.hidden_size, 1)
+        self.margin = margin
+        self.apply(self.init_weights)
+
+    def init_output(self):
+        """need to be called after from pretrained (model/itm.py:26-29)"""
+        self.rank_output.weight.data = self.itm_output.weight.data[1:, :]
+        self.rank_output.bias.data = self.itm_output.bias.data[1:]
+
+    def pooled(self, batch):
+        batch = defaultdict(lambda: None, batch)
+        sequence_output = self.uniter(batch["input_ids"], batch["position_ids"], batch["img_feat"],
+                                      batch["img_pos_feat"], batch["attn_masks"], batch["gather_index"],
+                                      output_all_encoded_layers=False)
+        return self.uniter.pooler(sequence_output)
+
+    def itm_scores(self, batch):
+        """model/pretrain.py:163-164: itm_output(pooler(sequence_output))."""
+        return self.itm_output(self.pooled(batch))
+
+    def forward(self, batch, compute_loss=True):
+        rank_scores = self.rank_output(self.pooled(batch))
+        if compute_loss:
+            scores = torch.sigmoid(rank_scores).contiguous().view(-1, batch["sample_size"])
+            pos, neg = scores[:, :1], scores[:, 1:]
+            return torch.clamp(self.margin + neg - pos, 0)
+        return rank_scores

@@ -310,9 +310,6 @@ def _bind():
         lib.ub200_gather_rows.restype = C.c_int
         lib.ub200_gather_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                           C.c_void_p]
-        lib.ub200_cvt_from_f32.restype = C.c_int
-        lib.ub200_cvt_from_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
-                                           C.c_void_p]
         _lib_ready = True
     return lib
 
@@ -451,52 +448,87 @@ class _EmbedFront(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dx):
+        """Row-kind masked LayerNorm backward (x4), img_linear wgrad on the tcgen05 GEMM, then the
+        table gradients in three launches (ub200_embed_bwd_scatter / _colsums); every small fp32
+        gradient lives in ONE staging buffer that is converted to the model dtype by one launch."""
         from . import ops
+        lib = _bind()
         idx, A, G, u, ppre, pos_feat, lnt_g, lni_g, lnp_g, lnf_g, img_w = ctx.saved_tensors
         dx = dx.contiguous()
         T, H = dx.shape
         dtype, dev = dx.dtype, dx.device
+        dt = _lib.dtype_code(dtype)
+        stream = _lib.current_stream()
         kind, word_id, pos_id, type_id, img_src, mask_flag = (idx[i] for i in range(6))
         kw = dict(dropout_p=ctx.dropout_p, rng_seed=ctx.seed, rng_stream=ctx.rng_stream,
                   row_kind=kind, dropout_on_dy=ctx.dropout_p > 0)
         word_shape, pos_shape, type_shape, posl_shape, mask_shape = ctx.shapes
-        du = torch.zeros_like(dx)
-        g = {}
-        if ctx.mode != 2:
-            _, _, g["lnt_g"], g["lnt_b"], _ = ops.layernorm_bwd(dx, u, lnt_g, kind=0, dx=du,
-                                                                want_dbias=False, **kw)
-        if ctx.mode != 1:
-            _, _, g["lnf_g"], g["lnf_b"], _ = ops.layernorm_bwd(dx, u, lnf_g, kind=1, dx=du,
-                                                                want_dbias=False, **kw)
-        d_type = torch.zeros(type_shape, device=dev, dtype=torch.float32)
-        d_type.index_add_(0, type_id.long(), du.float())
-        d_word = d_pos = None
-        if ctx.mode != 2:
-            du_txt = du * (kind == 0).unsqueeze(1)
+        has_txt, has_img = ctx.mode != 2, ctx.mode != 1
+        # ---- one fp32 staging buffer for every small gradient (accumulated by the kernels)
+        n_pos = pos_shape[0] * H if has_txt else 0
+        n_type = type_shape[0] * H
+        names = ["lnt_g", "lnt_b", "lnf_g", "lnf_b", "lni_g", "lni_b", "lnp_g", "lnp_b", "img_b", "posl_b"]
+        sizes = [n_pos, n_type] + [H] * len(names) + [H * 7]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + n)
+        S = torch.zeros(offs[-1], device=dev, dtype=torch.float32)
+        sec = {"pos": S[offs[0]:offs[1]], "type": S[offs[1]:offs[2]]}
+        for i, nme in enumerate(names):
+            sec[nme] = S[offs[2 + i]:offs[3 + i]]
+        sec["posl_w"] = S[offs[-2]:offs[-1]]
+
+        du = torch.empty_like(dx)        # every packed row is text or image: fully written below
+        if has_txt:
+            ops.layernorm_bwd(dx, u, lnt_g, kind=0, dx=du, want_dbias=False,
+                              dgamma=sec["lnt_g"], dbeta=sec["lnt_b"], **kw)
+        if has_img:
+            ops.layernorm_bwd(dx, u, lnf_g, kind=1, dx=du, want_dbias=False,
+                              dgamma=sec["lnf_g"], dbeta=sec["lnf_b"], **kw)
+        d_word = None
+        if has_txt:
             d_word = torch.zeros(word_shape, device=dev, dtype=dtype)
-            d_word.index_add_(0, word_id.long(), du_txt)
-            d_pos = torch.zeros(pos_shape, device=dev, dtype=torch.float32)
-            d_pos.index_add_(0, pos_id.long(), du_txt.float())
-        d_img_w = d_img_b = d_posl_w = d_posl_b = d_mask = None
-        if ctx.mode != 1:
-            dG, _, g["lni_g"], g["lni_b"], d_img_b = ops.layernorm_bwd(du, G, lni_g, row_kind=kind, kind=1)
-            dP, _, g["lnp_g"], g["lnp_b"], d_posl_b = ops.layernorm_bwd(du, ppre, lnp_g, row_kind=kind, kind=1)
+            _lib.check(lib.ub200_embed_bwd_scatter(du.data_ptr(), kind.data_ptr(), word_id.data_ptr(),
+                                                   pos_id.data_ptr(), d_word.data_ptr(),
+                                                   sec["pos"].data_ptr(), T, H, dt, stream))
+        ca = _lib.EmbedColsumArgs(x=du.data_ptr(), type_id=type_id.data_ptr(), out=sec["type"].data_ptr(),
+                                  T=T, hidden=H, mode=0, type_vocab=type_shape[0], dtype=dt)
+        _lib.check(lib.ub200_embed_bwd_colsums(C.byref(ca), stream))
+        d_img_w = d_mask = None
+        if has_img:
+            dG = torch.empty_like(dx)    # text rows are zeroed by the kernel (zero_inactive)
+            dP = torch.empty_like(dx)
+            ops.layernorm_bwd(du, G, lni_g, row_kind=kind, kind=1, dx=dG, zero_inactive=True,
+                              dgamma=sec["lni_g"], dbeta=sec["lni_b"], dbias=sec["img_b"])
+            ops.layernorm_bwd(du, ppre, lnp_g, row_kind=kind, kind=1, dx=dP, zero_inactive=True,
+                              dgamma=sec["lnp_g"], dbeta=sec["lnp_b"], dbias=sec["posl_b"])
             # img_linear.weight [H, D] = dG^T A   (wgrad form: both operands read un-transposed)
             d_img_w = ops.gemm(dG, A, a_major=1, b_major=1)
-            is_img = (kind == 1).unsqueeze(1)
-            F = (pos_feat[img_src.clamp(min=0).long()] * is_img).to(dtype)           # [T, 7]
-            d_posl_w = dP.t() @ F                                                   # [H, 7], K = T
+            # pos_linear.weight [H, 7] = dP^T box  (K = T reduction with 7 weights per row)
+            ca = _lib.EmbedColsumArgs(x=dP.data_ptr(), kind=kind.data_ptr(), img_src=img_src.data_ptr(),
+                                      pos_feat=pos_feat.data_ptr(), out=sec["posl_w"].data_ptr(),
+                                      T=T, hidden=H, mode=1, type_vocab=0, dtype=dt)
+            _lib.check(lib.ub200_embed_bwd_colsums(C.byref(ca), stream))
             if ctx.has_masks and ctx.needs_input_grad[25]:
                 dA = ops.gemm(dG, img_w, b_major=1)                                 # [T, D]
                 d_mask = torch.zeros(mask_shape, device=dev, dtype=dtype)
                 d_mask[1] = (dA.float() * (mask_flag != 0).unsqueeze(1)).sum(0).to(dtype)
-
-        def c(t):
-            return None if t is None else t.to(dtype)
+        # ---- fp32 -> model dtype, one launch; the returned gradients are views of S16
+        S16 = torch.empty(offs[-1], device=dev, dtype=dtype)
+        _lib.check(lib.ub200_cvt_from_f32_strided(S.data_ptr(), S16.data_ptr(), offs[-1], 1, 0, 0, 0, dt,
+                                                  stream))
+        g16 = {"pos": S16[offs[0]:offs[1]].view(pos_shape) if has_txt else None,
+               "type": S16[offs[1]:offs[2]].view(type_shape)}
+        for i, nme in enumerate(names):
+            g16[nme] = S16[offs[2 + i]:offs[3 + i]]
+        g16["posl_w"] = S16[offs[-2]:offs[-1]].view(posl_shape)
+        t_, i_ = has_txt, has_img
         return (None,) * 12 + (
-            d_word, c(d_pos), c(d_type), c(g.get("lnt_g")), c(g.get("lnt_b")),
-            d_img_w, c(d_img_b), c(g.get("lni_g")), c(g.get("lni_b")), c(g.get("lnp_g")), c(g.get("lnp_b")),
-            d_posl_w, c(d_posl_b), d_mask, c(g.get("lnf_g")), c(g.get("lnf_b")))
+            d_word, g16["pos"], g16["type"], g16["lnt_g"] if t_ else None, g16["lnt_b"] if t_ else None,
+            d_img_w, g16["img_b"] if i_ else None, g16["lni_g"] if i_ else None,
+            g16["lni_b"] if i_ else None, g16["lnp_g"] if i_ else None, g16["lnp_b"] if i_ else None,
+            g16["posl_w"] if i_ else None, g16["posl_b"] if i_ else None, d_mask,
+            g16["lnf_g"] if i_ else None, g16["lnf_b"] if i_ else None)
 
 
 class _EncoderStack(torch.autograd.Function):
@@ -720,10 +752,9 @@ class UniterModel(UniterPreTrainedModel):
         flat, small32, n = A["flat"], A["small32"], A["small_n"]
         dt = _lib.dtype_code(flat.dtype)
         stream = _lib.current_stream()
-        for i in range(lo, hi):
-            dst = flat[i * A["per_layer"] + A["big_n"]:(i + 1) * A["per_layer"]]
-            _lib.check(lib.ub200_cvt_from_f32(small32[i * n:(i + 1) * n].data_ptr(), dst.data_ptr(), n,
-                                              1 if accumulate else 0, dt, stream))
+        dst0 = flat[lo * A["per_layer"] + A["big_n"]:]
+        _lib.check(lib.ub200_cvt_from_f32_strided(small32[lo * n:].data_ptr(), dst0.data_ptr(), n, hi - lo,
+                                                  n, A["per_layer"], 1 if accumulate else 0, dt, stream))
         if not accumulate and lo == 0:
             for p, v in A["views"]:
                 if p.requires_grad:
@@ -814,16 +845,20 @@ class UniterModel(UniterPreTrainedModel):
         return meta
 
     # ------------------------------------------------------------------ forward
-    def forward(self, input_ids, position_ids, img_feat, img_pos_feat, attention_mask,
-                gather_index=None, img_masks=None, output_all_encoded_layers=True,
-                txt_type_ids=None, img_type_ids=None):
+    def encode_packed(self, input_ids, position_ids, img_feat, img_pos_feat, attention_mask,
+                      gather_index=None, img_masks=None, output_all_encoded_layers=False,
+                      txt_type_ids=None, img_type_ids=None):
+        """Same computation as forward() but returns the PACKED result and its bookkeeping:
+        (out, meta) with out [T, H] (or [NL, T, H]) over the valid tokens only and
+        meta["unpack_idx"] mapping a flat position b * L + j of the reference's [B, L] view to its
+        packed row (-1 at masked positions).  Heads that only read a few rows (MLM / MRM masked
+        positions, model/pretrain.py:129-133; the pooler's [:, 0]) gather them from here instead
+        of materialising the padded [B, L, H] tensor."""
         self._weight_table()  # validates dtype/device, packs q/k/v
-        dtype = self.encoder.layer[0].attention.self.query.weight.dtype
         meta = self._pack_meta(attention_mask)
         if meta["total"] == 0:
             raise ValueError("attention_mask selects no tokens")
         B, L = meta["batch"], meta["L"]
-        H = self.config.hidden_size
         # ---- embeddings (model/model.py:347-360) computed straight into PACKED rows by libub200
         if input_ids is None:
             mode = 2
@@ -858,9 +893,29 @@ class UniterModel(UniterPreTrainedModel):
         #  will need the per-layer activations)
         out = _EncoderStack.apply(x, self._anchor, self, meta, bool(output_all_encoded_layers),
                                   torch.is_grad_enabled())
+        return out, meta
 
+    def forward(self, input_ids, position_ids, img_feat, img_pos_feat, attention_mask,
+                gather_index=None, img_masks=None, output_all_encoded_layers=True,
+                txt_type_ids=None, img_type_ids=None):
+        out, meta = self.encode_packed(input_ids, position_ids, img_feat, img_pos_feat, attention_mask,
+                                       gather_index, img_masks, output_all_encoded_layers,
+                                       txt_type_ids, img_type_ids)
+        B, L = meta["batch"], meta["L"]
+        H = self.config.hidden_size
         # ---- back to the reference's padded [B, L, H] view (zeros at masked positions)
         if output_all_encoded_layers:
             return [_GatherRows.apply(out[l], meta["unpack_idx"], meta["total"],
                                       meta["pack_idx"]).view(B, L, H) for l in range(out.size(0))]
         return _GatherRows.apply(out, meta["unpack_idx"], meta["total"], meta["pack_idx"]).view(B, L, H)
+
+
+def gather_packed_rows(packed, rows):
+    """packed[rows] with zeros where rows < 0 (int32 [n]); differentiable.  The backward is itself
+    a row gather through the inverse map, so neither direction needs atomics or a sync."""
+    T = packed.size(0)
+    n = rows.numel()
+    inv = torch.full((T + 1,), -1, device=packed.device, dtype=torch.int32)
+    slot = torch.where(rows >= 0, rows, torch.full_like(rows, T)).long()
+    inv[slot] = torch.arange(n, device=packed.device, dtype=torch.int32)
+    return _GatherRows.apply(packed, rows.contiguous(), T, inv[:T].contiguous())

@@ -8,16 +8,19 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (EPI_ACCUM, EPI_BIAS, EPI_COLSUM, EPI_DGELU, EPI_DROPOUT, EPI_GELU,
+from ._lib import (EPI_ACCUM, EPI_ATOMIC, EPI_BIAS, EPI_COLSUM, EPI_DGELU, EPI_DROPOUT, EPI_GELU,
                    EPI_OUT_F32, EPI_RESIDUAL)
 
 
 def gemm(a, b, *, a_major=0, b_major=0, bias=None, residual=None, aux=None, out=None,
          gelu=False, dgelu=False, accumulate=False, out_fp32=False, colsum=None,
-         dropout_p=0.0, rng_seed=0, rng_stream=0, tile_n=0, max_ctas=0, cluster=0, _debug_flags=0):
+         dropout_p=0.0, rng_seed=0, rng_stream=0, tile_n=0, max_ctas=0, cluster=0, k_splits=0,
+         n_valid=0, _debug_flags=0):
     """D = epilogue(A . B^T) on the tcgen05 GEMM core.  Returns `out` (and pre-activation if gelu).
 
     a: [M,K] (a_major=0) or [K,M] (a_major=1);  b: [N,K] (b_major=0) or [K,N] (b_major=1).
+    k_splits > 1 (or -1 = fill the SMs): split-K into a zero-initialised fp32 `out` through atomics.
+    n_valid: b holds only n_valid of the N (= out.size(1)) output features; the rest get acc = 0.
     """
     lib = _lib.load()
     assert a.is_cuda and b.is_cuda and a.dtype == b.dtype
@@ -31,8 +34,15 @@ def gemm(a, b, *, a_major=0, b_major=0, bias=None, residual=None, aux=None, out=
     else:
         Kb, N = b.shape
     assert K == Kb, "contraction mismatch %d vs %d" % (K, Kb)
+    if n_valid:
+        assert n_valid == N, "n_valid is the number of output features b really holds"
+        N = out.size(1) if out is not None else (N + 7) // 8 * 8
+    splitk = k_splits > 1 or k_splits == -1
     if out is None:
-        out = torch.empty(M, N, device=a.device, dtype=torch.float32 if out_fp32 else a.dtype)
+        if splitk:
+            out = torch.zeros(M, N, device=a.device, dtype=torch.float32)
+        else:
+            out = torch.empty(M, N, device=a.device, dtype=torch.float32 if out_fp32 else a.dtype)
     out2 = torch.empty(M, N, device=a.device, dtype=a.dtype) if gelu else None
     epi = 0
     if bias is not None:
@@ -51,6 +61,9 @@ def gemm(a, b, *, a_major=0, b_major=0, bias=None, residual=None, aux=None, out=
         epi |= EPI_OUT_F32
     if colsum is not None:
         epi |= EPI_COLSUM
+    if splitk:
+        assert out.dtype == torch.float32 and epi == EPI_OUT_F32, "split-K: fp32 out, no other epilogue"
+        epi |= EPI_ATOMIC
     epi |= _debug_flags
     args = _lib.GemmArgs(
         a=a.data_ptr(), b=b.data_ptr(), lda=a.stride(0), ldb=b.stride(0),
@@ -62,7 +75,8 @@ def gemm(a, b, *, a_major=0, b_major=0, bias=None, residual=None, aux=None, out=
         ldaux=aux.stride(0) if aux is not None else 0,
         ldo=out.stride(0),
         dropout_p=float(dropout_p), rng_seed=int(rng_seed), rng_stream=int(rng_stream),
-        tile_n=int(tile_n), max_ctas=int(max_ctas), cluster=int(cluster))
+        tile_n=int(tile_n), max_ctas=int(max_ctas), cluster=int(cluster), k_splits=int(k_splits),
+        n_valid=int(n_valid))
     _lib.check(lib.ub200_gemm(C.byref(args), _lib.current_stream()))
     return (out, out2) if gelu else out
 
@@ -112,7 +126,8 @@ def layernorm_fwd(x, gamma, beta):
 
 
 def layernorm_bwd(dy, x, gamma, dropout_p=0.0, rng_seed=0, rng_stream=0, want_dbias=True,
-                  row_kind=None, kind=0, dropout_on_dy=False, dx=None, dgamma=None, dbeta=None, dbias=None):
+                  row_kind=None, kind=0, dropout_on_dy=False, dx=None, dgamma=None, dbeta=None, dbias=None,
+                  zero_inactive=False):
     """Returns dx, dx_drop (or None), dgamma, dbeta, dbias (fp32)."""
     lib = _lib.load()
     rows, H = x.shape
@@ -129,7 +144,8 @@ def layernorm_bwd(dy, x, gamma, dropout_p=0.0, rng_seed=0, rng_stream=0, want_db
                        dx_drop=_lib.ptr(dx_drop), dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(),
                        dbias=_lib.ptr(dbias), rows=rows, hidden=H, dtype=_lib.dtype_code(x.dtype),
                        dropout_p=float(dropout_p), rng_seed=int(rng_seed), rng_stream=int(rng_stream),
-                       row_kind=_lib.ptr(row_kind), kind=int(kind), dropout_on_dy=1 if dropout_on_dy else 0)
+                       row_kind=_lib.ptr(row_kind), kind=int(kind),
+                       dropout_on_dy=(1 if dropout_on_dy else 0) | (2 if zero_inactive else 0))
     _lib.check(lib.ub200_layernorm_bwd(C.byref(a), _lib.current_stream()))
     return dx, dx_drop, dgamma, dbeta, dbias
 
@@ -142,3 +158,63 @@ def colsum(x, out=None):
     _lib.check(lib.ub200_colsum(x.data_ptr(), out.data_ptr(), rows, N, x.stride(0),
                                 _lib.dtype_code(x.dtype), _lib.current_stream()))
     return out
+
+
+def cvt_from_f32(src, dtype, out=None, accumulate=False):
+    """16-bit copy of an fp32 tensor (one launch)."""
+    lib = _lib.load()
+    src = src.contiguous()
+    if out is None:
+        out = torch.empty(src.shape, device=src.device, dtype=dtype)
+    if src.numel():
+        _lib.check(lib.ub200_cvt_from_f32(src.data_ptr(), out.data_ptr(), src.numel(),
+                                          1 if accumulate else 0, _lib.dtype_code(dtype),
+                                          _lib.current_stream()))
+    return out
+
+
+def ce_fwd(logits, targets, vocab):
+    """loss [n] fp32, lse [n] fp32 of softmax cross-entropy over logits[:, :vocab] (16-bit, row
+    pitch a multiple of 8)."""
+    lib = _lib.load()
+    n = logits.size(0)
+    loss = torch.empty(n, device=logits.device, dtype=torch.float32)
+    lse = torch.empty(n, device=logits.device, dtype=torch.float32)
+    assert targets.dtype == torch.int64 and targets.is_contiguous() and logits.stride(1) == 1
+    _lib.check(lib.ub200_ce_fwd(logits.data_ptr(), logits.stride(0), targets.data_ptr(), loss.data_ptr(),
+                                lse.data_ptr(), n, vocab, _lib.dtype_code(logits.dtype),
+                                _lib.current_stream()))
+    return loss, lse
+
+
+def ce_bwd_(logits, targets, lse, dloss, vocab):
+    """In place: logits[:, c] <- (softmax - onehot) * dloss for c < vocab, 0 for the padding columns."""
+    lib = _lib.load()
+    n, ncols = logits.shape
+    assert dloss.dtype == torch.float32 and dloss.is_contiguous()
+    _lib.check(lib.ub200_ce_bwd(logits.data_ptr(), logits.data_ptr(), logits.stride(0), targets.data_ptr(),
+                                lse.data_ptr(), dloss.data_ptr(), n, vocab, ncols,
+                                _lib.dtype_code(logits.dtype), _lib.current_stream()))
+    return logits
+
+
+def dgelu_mul(dy, pre):
+    lib = _lib.load()
+    out = torch.empty_like(dy)
+    assert dy.is_contiguous() and pre.is_contiguous() and dy.numel() % 8 == 0
+    _lib.check(lib.ub200_dgelu_mul(dy.data_ptr(), pre.data_ptr(), out.data_ptr(), dy.numel(),
+                                   _lib.dtype_code(dy.dtype), _lib.current_stream()))
+    return out
+
+
+def gather_rows(src, index, rows=None):
+    """dst[r] = src[index[r]] if index[r] >= 0 else 0 (int32 index; bit-exact row mover)."""
+    lib = _lib.load()
+    src = src.contiguous()
+    rows = index.numel() if rows is None else rows
+    H = src.size(-1)
+    dst = torch.empty(rows, H, device=src.device, dtype=src.dtype)
+    if rows:
+        _lib.check(lib.ub200_gather_rows(src.data_ptr(), dst.data_ptr(), index.data_ptr(), rows,
+                                         H * src.element_size(), _lib.current_stream()))
+    return dst
