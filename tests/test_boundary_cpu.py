@@ -69,11 +69,14 @@ def test_ctypes_mirrors_match_the_header_layout():
     from uniter_b200.model import _EncoderDesc, _LayerGrads, _LayerWeights
     prog = r'''
     #include <stdio.h>
+    #include <stddef.h>
     #include "ub200.h"
     int main(void) {
-      printf("%zu %zu %zu %zu %zu %zu\n", sizeof(ub200_gemm_args), sizeof(ub200_attn_args),
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ub200_gemm_args), sizeof(ub200_attn_args),
              sizeof(ub200_ln_bwd_args), sizeof(ub200_layer_weights), sizeof(ub200_layer_grads),
-             sizeof(ub200_encoder_desc));
+             sizeof(ub200_encoder_desc), sizeof(ub200_adam_segment), sizeof(ub200_embed_colsum_args),
+             offsetof(ub200_gemm_args, k_splits), offsetof(ub200_gemm_args, n_valid),
+             offsetof(ub200_adam_segment, step_size), offsetof(ub200_embed_colsum_args, T));
       return 0;
     }'''
     with tempfile.TemporaryDirectory() as d:
@@ -83,7 +86,10 @@ def test_ctypes_mirrors_match_the_header_layout():
         subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     mine = [C.sizeof(_lib.GemmArgs), C.sizeof(_lib.AttnArgs), C.sizeof(_lib.LnBwdArgs),
-            C.sizeof(_LayerWeights), C.sizeof(_LayerGrads), C.sizeof(_EncoderDesc)]
+            C.sizeof(_LayerWeights), C.sizeof(_LayerGrads), C.sizeof(_EncoderDesc),
+            C.sizeof(_lib.AdamSegment), C.sizeof(_lib.EmbedColsumArgs),
+            _lib.GemmArgs.k_splits.offset, _lib.GemmArgs.n_valid.offset,
+            _lib.AdamSegment.step_size.offset, _lib.EmbedColsumArgs.T.offset]
     assert sizes == mine, (sizes, mine)
 
 

@@ -97,7 +97,8 @@ def test_gemm_rejects_bad_arguments():
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("accumulate", [False, True])
-def test_grouped_wgrad_matches_separate_gemms(dtype, accumulate):
+@pytest.mark.parametrize("tn", [0, 128, 192, 256])
+def test_grouped_wgrad_matches_separate_gemms(dtype, accumulate, tn):
     """ub200_gemm_grouped: the four weight-gradient shapes of a base layer in one launch."""
     import ctypes as C
     from uniter_b200 import _lib
@@ -116,7 +117,8 @@ def test_grouped_wgrad_matches_separate_gemms(dtype, accumulate):
         keep += [a, b]; outs.append(out); refs.append(ref)
         args[i] = _lib.GemmArgs(a=a.data_ptr(), b=b.data_ptr(), lda=M, ldb=N, a_major=1, b_major=1,
                                 M=M, N=N, K=T, dtype=_lib.dtype_code(dtype),
-                                epilogue=_lib.EPI_ACCUM if accumulate else 0, out=out.data_ptr(), ldo=N)
+                                epilogue=_lib.EPI_ACCUM if accumulate else 0, out=out.data_ptr(), ldo=N,
+                                tile_n=tn)
     _lib.check(lib.ub200_gemm_grouped(args, 4, _lib.current_stream()))
     torch.cuda.synchronize()
     for out, ref in zip(outs, refs):

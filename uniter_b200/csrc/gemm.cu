@@ -1,5 +1,7 @@
 // C entry point of the tcgen05 GEMM core: argument checks, tile / cluster selection, TMA
 // descriptors.  Device code lives in gemm_impl.cuh (instantiated in gemm_bf16.cu / gemm_f16.cu).
+#include <stdlib.h>
+
 #include "common.h"
 
 #include "gemm_params.h"
@@ -148,7 +150,6 @@ extern "C" int ub200_gemm_grouped(const ub200_gemm_args* args, int32_t count, ub
   struct { CUtensorMap a[GEMM_MAX_GROUP]; CUtensorMap b[GEMM_MAX_GROUP]; } tm;
   GroupedParams g{};
   g.nprob = count; g.K = args[0].K; g.epilogue = args[0].epilogue;
-  int tiles = 0;
   for (int i = 0; i < count; ++i) {
     const ub200_gemm_args& a = args[i];
     UB_CHECK_ARG(a.a && a.b && a.out, "gemm_grouped[%d]: null operand", i);
@@ -157,18 +158,43 @@ extern "C" int ub200_gemm_grouped(const ub200_gemm_args* args, int32_t count, ub
                  "gemm_grouped[%d]: K / dtype / epilogue must match problem 0", i);
     UB_CHECK_ARG(a.M > 0 && a.N > 0 && a.K > 0 && a.N % 8 == 0 && a.ldo % 8 == 0,
                  "gemm_grouped[%d]: bad shape", i);
+  }
+  // N tile shared by the group: fewest (rounds over the SMs) x (measured cycles per k-block of a
+  // 128 x bn tile, see pick_config) — 4 base-layer wgrads: 432 tiles of 128 = 3 rounds x 583,
+  // 288 tiles of 192 = 2 rounds x 665, 216 tiles of 256 = 2 rounds x 745.
+  const int sms = num_sms();
+  int bn = args[0].tile_n;
+  if (bn == 0) {
+    static const int env_bn = [] { const char* e = getenv("UB200_GROUP_BN"); return e ? atoi(e) : 0; }();
+    bn = env_bn;
+  }
+  if (bn == 0) {
+    double best = 1e30;
+    const int cand[3] = {128, 192, 256};
+    for (int c = 0; c < 3; ++c) {
+      int t = 0;
+      for (int i = 0; i < count; ++i) t += ((args[i].M + BM - 1) / BM) * ((args[i].N + cand[c] - 1) / cand[c]);
+      const double cost = static_cast<double>((t + sms - 1) / sms) * (421.0 + 1.27 * cand[c]);
+      if (cost < best - 1e-9) { best = cost; bn = cand[c]; }
+    }
+  }
+  UB_CHECK_ARG(bn == 128 || bn == 192 || bn == 256, "gemm_grouped: tile_n must be 0, 128, 192 or 256 (got %d)", bn);
+  g.bn = bn;
+  int tiles = 0;
+  for (int i = 0; i < count; ++i) {
+    const ub200_gemm_args& a = args[i];
     int rc = make_tma_2d(&tm.a[i], a.a, a.dtype, a.K, a.M, a.lda, BK, 64);
     if (rc) return rc;
     rc = make_tma_2d(&tm.b[i], a.b, a.dtype, a.K, a.N, a.ldb, BK, 64);
     if (rc) return rc;
     g.M[i] = a.M; g.N[i] = a.N; g.out[i] = a.out; g.ldo[i] = a.ldo;
-    g.tiles_n[i] = (a.N + 127) / 128;
+    g.tiles_n[i] = (a.N + bn - 1) / bn;
     g.tile_start[i] = tiles;
     tiles += ((a.M + BM - 1) / BM) * g.tiles_n[i];
   }
   for (int i = count; i <= GEMM_MAX_GROUP; ++i) g.tile_start[i] = tiles;
   for (int i = count; i < GEMM_MAX_GROUP; ++i) { tm.a[i] = tm.a[0]; tm.b[i] = tm.b[0]; }
-  int grid = num_sms();
+  int grid = sms;
   if (grid > tiles) grid = tiles;
   if (args[0].dtype == UB200_BF16) return gemm_group_dispatch_bf16(&tm, g, grid, stream);
   return gemm_group_dispatch_f16(&tm, g, grid, stream);

@@ -459,10 +459,9 @@ __device__ __forceinline__ int group_of_tile(const GroupedParams& g, int tile) {
   return pi;
 }
 
-template <bool kBF16, int EPI>
+template <int BN, bool kBF16, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_group_kernel(const __grid_constant__ TmPack tm, const GroupedParams g) {
-  constexpr int BN = 128;
   using Cfg = GemmCfg<BN, 1>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -811,14 +810,14 @@ int gemm_dispatch(int bn, int cluster, int a_major, int b_major, const GemmParam
   return set_error(UB200_EINVAL, "gemm: tile_n must be 0, 64, 128, 192 or 256 (got %d)", bn);
 }
 
-template <bool kBF16>
-int gemm_group_dispatch(const TmPack& tm, const GroupedParams& g, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<128, 1>;
+template <int BN, bool kBF16>
+int gemm_group_launch(const TmPack& tm, const GroupedParams& g, int grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, 1>;
   void (*kern)(const TmPack, const GroupedParams);
-  if (g.epilogue == 0) kern = gemm_group_kernel<kBF16, 0>;
-  else if (g.epilogue == UB200_EPI_ACCUM) kern = gemm_group_kernel<kBF16, UB200_EPI_ACCUM>;
+  if (g.epilogue == 0) kern = gemm_group_kernel<BN, kBF16, 0>;
+  else if (g.epilogue == UB200_EPI_ACCUM) kern = gemm_group_kernel<BN, kBF16, UB200_EPI_ACCUM>;
   else return set_error(UB200_EUNSUPPORTED, "gemm_grouped: epilogue must be 0 or ACCUM");
-  static bool configured[2] = {false, false};
+  static bool configured[2] = {false, false};   // per instantiation
   const int ci = g.epilogue ? 1 : 0;
   if (!configured[ci]) {
     UB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -827,6 +826,16 @@ int gemm_group_dispatch(const TmPack& tm, const GroupedParams& g, int grid, cuda
   ProfScope ps(stream);
   UB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, 1, tm, g));
   return 0;
+}
+
+template <bool kBF16>
+int gemm_group_dispatch(const TmPack& tm, const GroupedParams& g, int grid, cudaStream_t stream) {
+  switch (g.bn) {
+    case 128: return gemm_group_launch<128, kBF16>(tm, g, grid, stream);
+    case 192: return gemm_group_launch<192, kBF16>(tm, g, grid, stream);
+    case 256: return gemm_group_launch<256, kBF16>(tm, g, grid, stream);
+  }
+  return set_error(UB200_EINVAL, "gemm_grouped: tile_n must be 128, 192 or 256 (got %d)", g.bn);
 }
 
 }  // namespace ub

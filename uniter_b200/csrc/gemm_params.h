@@ -31,6 +31,7 @@ struct GemmParams {
 constexpr int GEMM_MAX_GROUP = 4;
 struct GroupedParams {
   int nprob, K, epilogue;
+  int bn;                               // N tile of every problem: 128, 192 or 256
   int M[GEMM_MAX_GROUP], N[GEMM_MAX_GROUP];
   void* out[GEMM_MAX_GROUP];
   long long ldo[GEMM_MAX_GROUP];
