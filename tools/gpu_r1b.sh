@@ -13,6 +13,11 @@ timeout -k 10 150 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpur
 echo "bench default exit=$?"; cut -c1-400 gpurun_out/bench_default.json; tail -3 gpurun_out/bench_default.err
 UB200_GROUP_BN=128 timeout -k 10 150 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-profile > gpurun_out/bench_group128.json 2> gpurun_out/bench_group128.err
 echo "bench group128 exit=$?"; cut -c1-250 gpurun_out/bench_group128.json
+for v in 2 3; do
+  UB200_LN_BWD_CTAS_PER_SM=$v timeout -k 10 150 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_lnbwd$v.json 2> gpurun_out/bench_lnbwd$v.err
+  echo "bench lnbwd$v exit=$?"; cut -c1-250 gpurun_out/bench_lnbwd$v.json
+done
+timeout -k 10 120 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit=$?"; tail -2 gpurun_out/smoke.log
 if [ "${1:-}" = "ncu" ]; then
   CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile"
   timeout -k 5 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,lts__t_bytes.sum --clock-control none -s 1500 -c 800 --csv --log-file gpurun_out/step_metrics.csv $CMD > gpurun_out/ncu_step.log 2>&1

@@ -9,6 +9,8 @@
 //   cvt           16-bit <- fp32 (+ optional accumulate): small-gradient finalisation
 // One warp per row; a lane owns the same columns in every row it visits so that the column
 // reductions of ln_bwd stay in registers until one smem + atomic step per CTA.
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -404,7 +406,10 @@ int launch_ln_bwd(int dtype, const LnBwdParams& p, cudaStream_t stream) {
     return set_error(UB200_EUNSUPPORTED, "ln_bwd: need rows > 0, H %% 8 == 0 and H <= %d (H=%d)",
                      LN_MAX_VEC * 256, p.H);
   int grid = (p.rows + 7) / 8;
-  const int cap = num_sms();   // one wave, one CTA per SM
+  // one wave; UB200_LN_BWD_CTAS_PER_SM (default 1) trades more column-sum atomics for more
+  // rows in flight per SM
+  static const int per_sm = [] { const char* e = getenv("UB200_LN_BWD_CTAS_PER_SM"); int v = e ? atoi(e) : 1; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
+  const int cap = num_sms() * per_sm;
   if (grid > cap) grid = cap;
   ProfScope ps(stream);
   if (dtype == UB200_BF16) UB_CHECK_CUDA(launch_ln_bwd_nv<true>(p, grid, stream));
