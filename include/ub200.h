@@ -108,7 +108,7 @@ typedef struct {
   const void* aux;         /* [M, N] 16-bit, pitch ldaux (pre-activation for DGELU) */
   void* out;               /* [M, N], pitch ldo */
   void* out2;              /* [M, N] 16-bit, pitch ldo (pre-activation, GELU only) */
-  float* colsum;           /* [N] fp32, accumulated with atomics */
+  float* colsum;           /* [N] fp32, accumulated with (16-byte vector) atomics: 16-byte aligned */
   int64_t ldr, ldaux, ldo;
   float dropout_p;         /* 0 <= p < 1 */
   uint64_t rng_seed;       /* Philox key */
@@ -182,7 +182,7 @@ typedef struct {
   const void* gamma;  /* [hidden] */
   void* dx;           /* [rows, hidden] */
   void* dx_drop;      /* [rows, hidden] dx * mask / keep, required iff dropout_p > 0 */
-  float* dgamma;      /* [hidden] fp32, accumulated */
+  float* dgamma;      /* [hidden] fp32, accumulated; dgamma / dbeta / dbias 16-byte aligned */
   float* dbeta;       /* [hidden] fp32, accumulated */
   float* dbias;       /* [hidden] fp32 column sum of the Linear-branch gradient, or NULL */
   int32_t rows, hidden, dtype;

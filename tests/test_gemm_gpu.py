@@ -165,7 +165,7 @@ def test_gemm_n_valid_over_unpadded_weight(dtype, M, V, K):
     ref = x.float() @ w.float().t() + bias[:V].float()
     _close(out[:, :V], ref, TOL[dtype], "n_valid forward")
     if Vp != V:
-        assert (out[:, V:].float() == -30000.0).all()
+        assert (out[:, V:] == bias[V:]).all()          # acc = 0 exactly, bias only
     # wgrad over the same padded buffer: A = out[:, :V] read MN-major with row pitch Vp
     z = torch.randn(M, K, device="cuda").to(dtype)
     d = (torch.randn(M, Vp, device="cuda") * 0.1).to(dtype)

@@ -449,3 +449,27 @@ def test_full_size_c2_forward_vs_oracle_and_batch_invariance():
             alone = _fwd(model, one, output_all_encoded_layers=False).float().cpu()
         d = (alone[0] - out[k, :tl + nb]).abs().max().item()
         assert d <= 1e-2, (k, d)
+
+
+def test_pack_meta_cache_is_bound_to_the_tensor_object_not_its_address():
+    """The caching allocator gives a freed mask's block to the next mask of the same shape: an
+    address-keyed length cache would silently pack the new batch with the old lengths."""
+    from uniter_b200.model import UniterModel, register_lengths
+    m1 = torch.ones(2, 56, dtype=torch.long, device="cuda")
+    assert UniterModel._pack_meta(m1)["lens_host"] == [56, 56]
+    ptr = m1.data_ptr()
+    del m1
+    m2 = torch.zeros(2, 56, dtype=torch.long, device="cuda")
+    m2[0, :56] = 1
+    m2[1, :44] = 1
+    same_block = m2.data_ptr() == ptr          # the hazardous case (usually true)
+    meta = UniterModel._pack_meta(m2)
+    assert meta["lens_host"] == [56, 44] and meta["total"] == 100, (same_block, meta["lens_host"])
+    assert UniterModel._pack_meta(m2) is meta  # same object, same version: cached
+    m2[1, 44:50] = 1                           # in-place edit bumps the version: recomputed
+    assert UniterModel._pack_meta(m2)["lens_host"] == [56, 50]
+    # host-registered lengths are honoured for the registered object only
+    m3 = m2.clone()
+    register_lengths(m3, [56, 50], prefix=True)
+    assert UniterModel._pack_meta(m3)["total"] == 106
+    assert torch.equal(UniterModel._pack_meta(m3)["pack_idx"], UniterModel._pack_meta(m2)["pack_idx"])

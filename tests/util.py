@@ -72,12 +72,15 @@ def head_state(module, seed, ties=()):
     parameter that the reference ties under a second name ends up with the value of the key that
     is loaded LAST — `ties` lists (our key, reference alias loaded later)."""
     from uniter_b200.synth import seeded_state
-    shapes = {k: tuple(v.shape) for k, v in module.state_dict().items()}
+    own = {k: tuple(v.shape) for k, v in module.state_dict().items()}
+    shapes = dict(own)
     for ours, alias in ties:
         shapes[alias] = shapes[ours]
     st = seeded_state(shapes, seed=seed)
     for ours, alias in ties:
-        st[ours] = st.pop(alias)
+        st[ours] = st[alias]
+        if alias not in own:          # the alias only exists in the reference module
+            del st[alias]
     return st
 
 

@@ -57,7 +57,8 @@ extern "C" int ub200_gemm(const ub200_gemm_args* args, ub200_stream_t stream_) {
   UB_CHECK_ARG(!(epi & UB200_EPI_GELU) || a.out2, "gemm: EPI_GELU without out2");
   UB_CHECK_ARG(!(epi & UB200_EPI_DGELU) || (a.aux && a.ldaux % 8 == 0),
                "gemm: EPI_DGELU needs aux with ldaux %% 8 == 0");
-  UB_CHECK_ARG(!(epi & UB200_EPI_COLSUM) || a.colsum, "gemm: EPI_COLSUM without colsum");
+  UB_CHECK_ARG(!(epi & UB200_EPI_COLSUM) || (a.colsum && (reinterpret_cast<uintptr_t>(a.colsum) & 15) == 0),
+               "gemm: EPI_COLSUM needs a 16-byte aligned colsum (vector atomics)");
   UB_CHECK_ARG(!((epi & UB200_EPI_GELU) && (epi & UB200_EPI_OUT_F32)),
                "gemm: EPI_GELU with fp32 output is not supported");
   UB_CHECK_ARG(a.dropout_p >= 0.f && a.dropout_p < 1.f, "gemm: dropout_p out of range");

@@ -257,9 +257,9 @@ __device__ __forceinline__ void epilogue_warp(const GemmParams& p, uint32_t t_ac
         x += __shfl_xor_sync(0xffffffffu, x, 16);
         csum[i] = x;
       }
-      if (lane < 4 && col_ok) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(p.colsum + col + i, csum[i]);
+      if (lane < 4 && col_ok) {        // two 16-byte vector atomics instead of eight scalar ones
+        atomicAdd(reinterpret_cast<float4*>(p.colsum + col), make_float4(csum[0], csum[1], csum[2], csum[3]));
+        atomicAdd(reinterpret_cast<float4*>(p.colsum + col + 4), make_float4(csum[4], csum[5], csum[6], csum[7]));
       }
     }
   }

@@ -267,16 +267,23 @@ ln_bwd_kernel(const LnBwdParams p) {
       red[2][warp][lane * 8 + e] = acc_d[i][e];
     }
     __syncthreads();
-    const int colslot = threadIdx.x;  // 256 threads <-> the 256 columns of this slot
-    const int col = colslot + i * 256;
-    if (col < H) {
-      float a = 0.f, b = 0.f, d = 0.f;
-      for (int w = 0; w < nwarps; ++w) {
-        a += red[0][w][colslot]; b += red[1][w][colslot]; d += red[2][w][colslot];
+    // 64 threads x 4 consecutive columns: one 16-byte vector atomic per quantity instead of four
+    // scalar ones (the column-sum atomics of 148 CTAs were ~1/3 of this kernel's time)
+    if (threadIdx.x < 64) {
+      const int c4 = threadIdx.x * 4;
+      const int col = c4 + i * 256;
+      if (col < H) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f}, d[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int w = 0; w < nwarps; ++w) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            a[q] += red[0][w][c4 + q]; b[q] += red[1][w][c4 + q]; d[q] += red[2][w][c4 + q];
+          }
+        }
+        atomicAdd(reinterpret_cast<float4*>(p.dgamma + col), make_float4(a[0], a[1], a[2], a[3]));
+        atomicAdd(reinterpret_cast<float4*>(p.dbeta + col), make_float4(b[0], b[1], b[2], b[3]));
+        if (p.dbias) atomicAdd(reinterpret_cast<float4*>(p.dbias + col), make_float4(d[0], d[1], d[2], d[3]));
       }
-      atomicAdd(p.dgamma + col, a);
-      atomicAdd(p.dbeta + col, b);
-      if (p.dbias) atomicAdd(p.dbias + col, d);
     }
   }
 }
@@ -328,13 +335,17 @@ colsum_kernel(const void* __restrict__ x_, float* __restrict__ out, int rows, in
 #pragma unroll
   for (int e = 0; e < 8; ++e) red[rl][cv * 8 + e] = acc[e];
   __syncthreads();
-  const int c = threadIdx.x;
-  const int col = blockIdx.x * 256 + c;
-  if (col < N) {
-    float s = 0.f;
+  if (threadIdx.x < 64) {            // 4 consecutive columns per thread: one vector atomic
+    const int c4 = threadIdx.x * 4;
+    const int col = blockIdx.x * 256 + c4;
+    if (col < N) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[w][c];
-    atomicAdd(out + col, s);
+      for (int w = 0; w < 8; ++w)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s[q] += red[w][c4 + q];
+      atomicAdd(reinterpret_cast<float4*>(out + col), make_float4(s[0], s[1], s[2], s[3]));
+    }
   }
 }
 
@@ -493,6 +504,9 @@ extern "C" int ub200_layernorm_fwd(const void* x, const void* gamma, const void*
 extern "C" int ub200_layernorm_bwd(const ub200_ln_bwd_args* a, ub200_stream_t stream) {
   UB_CHECK_ARG(a && a->dy && a->x && a->gamma && a->dx && a->dgamma && a->dbeta,
                "layernorm_bwd: null pointer");
+  UB_CHECK_ARG(((reinterpret_cast<uintptr_t>(a->dgamma) | reinterpret_cast<uintptr_t>(a->dbeta) |
+                 reinterpret_cast<uintptr_t>(a->dbias)) & 15) == 0,
+               "layernorm_bwd: dgamma / dbeta / dbias must be 16-byte aligned (vector atomics)");
   ub::LnBwdParams p{};
   p.dy = a->dy; p.x = a->x; p.gamma = a->gamma; p.dx = a->dx;
   p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.dbias = a->dbias;
@@ -527,6 +541,7 @@ extern "C" int ub200_gather_rows(const void* src, void* dst, const int32_t* inde
 extern "C" int ub200_colsum(const void* x, float* out, int32_t rows, int32_t cols, int64_t ld,
                             int32_t dtype, ub200_stream_t stream) {
   UB_CHECK_ARG(x && out, "colsum: null pointer");
+  UB_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "colsum: out must be 16-byte aligned (vector atomics)");
   return ub::launch_colsum(dtype, x, out, rows, cols, static_cast<int>(ld),
                            reinterpret_cast<cudaStream_t>(stream));
 }

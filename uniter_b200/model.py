@@ -19,6 +19,7 @@ import ctypes as C
 import json
 import logging
 import math
+import weakref
 
 import torch
 from torch import nn
@@ -318,17 +319,37 @@ _rng_offset = [0]
 _META_CACHE = {}
 
 
+def _meta_key(t):
+    return (t._version, t.size(0), t.size(1))
+
+
+def _meta_lookup(t):
+    """Cache entry for THIS tensor object (weak reference + version), never for whatever tensor
+    happens to live at the same address: the caching allocator hands the block of a freed mask to
+    the next mask of the same shape, so an address-keyed cache would serve stale lengths."""
+    hit = _META_CACHE.get(id(t))
+    if hit is not None and hit[0]() is t and hit[1] == _meta_key(t):
+        return hit[2]
+    return None
+
+
+def _meta_store(t, meta):
+    if len(_META_CACHE) > 64:
+        for k in [k for k, v in _META_CACHE.items() if v[0]() is None]:
+            del _META_CACHE[k]
+        if len(_META_CACHE) > 64:
+            _META_CACHE.clear()
+    _META_CACHE[id(t)] = (weakref.ref(t), _meta_key(t), meta)
+
+
 def register_lengths(attention_mask_dev, lens_host, prefix=False):
     """Tell the model the per-sample valid lengths of a device attention mask that the host
     already knows (the loader computed them before the H2D copy), so forward() does not have to
-    read them back.  Keyed by the mask tensor's address + version.  `prefix=True` additionally
-    asserts that the mask is a prefix mask ([1]*S_b + [0]*(L-S_b), what every reference collate
-    emits, e.g. data/vqa.py:39,53): the pack indices are then computed arithmetically."""
-    B, L = attention_mask_dev.shape
-    key = (attention_mask_dev.data_ptr(), attention_mask_dev._version, B, L)
-    if len(_META_CACHE) > 64:
-        _META_CACHE.clear()
-    _META_CACHE[key[0]] = (key, {"lens_host": [int(v) for v in lens_host], "prefix": bool(prefix)})
+    read them back.  Bound to this tensor OBJECT (and its version): pass the same object to
+    forward().  `prefix=True` additionally asserts that the mask is a prefix mask
+    ([1]*S_b + [0]*(L-S_b), what every reference collate emits, e.g. data/vqa.py:39,53): the pack
+    indices are then computed arithmetically."""
+    _meta_store(attention_mask_dev, {"lens_host": [int(v) for v in lens_host], "prefix": bool(prefix)})
 
 
 # ============================================================================ autograd glue
@@ -805,15 +826,14 @@ class UniterModel(UniterPreTrainedModel):
         32-pair train forwards of model/itm.py:82-88 reuse it), or one small device->host read
         (the reference itself syncs every step, train_vqa.py:201)."""
         B, L = attention_mask.shape
-        key = (attention_mask.data_ptr(), attention_mask._version, B, L)
-        hit = _META_CACHE.get(key[0])
-        if hit is not None and hit[0] == key and "cu_seqlens" in hit[1]:
-            return hit[1]
+        hit = _meta_lookup(attention_mask)
+        if hit is not None and "cu_seqlens" in hit:
+            return hit
         dev = attention_mask.device
-        registered = hit is not None and hit[0] == key
-        if registered and hit[1].get("prefix"):
+        registered = hit is not None
+        if registered and hit.get("prefix"):
             # prefix masks with host-known lengths: everything from arithmetic, no device reads
-            lens_h = hit[1]["lens_host"]
+            lens_h = hit["lens_host"]
             T = int(sum(lens_h))
             cu_h = [0]
             for v in lens_h:
@@ -827,7 +847,7 @@ class UniterModel(UniterPreTrainedModel):
             am = attention_mask != 0
             lens = am.sum(1)
             if registered:
-                lens_h = hit[1]["lens_host"]          # registered by the loader: no sync
+                lens_h = hit["lens_host"]             # registered by the loader: no sync
             else:
                 lens_h = lens.tolist()                # host sync (B integers)
             T = int(sum(lens_h))
@@ -839,9 +859,7 @@ class UniterModel(UniterPreTrainedModel):
         unpack_idx[pack_idx.long()] = torch.arange(T, device=dev, dtype=torch.int32)
         meta = dict(batch=B, L=L, total=T, max_seqlen=max(lens_h) if lens_h else 0,
                     cu_seqlens=cu, pack_idx=pack_idx, unpack_idx=unpack_idx, lens_host=lens_h)
-        if len(_META_CACHE) > 64:
-            _META_CACHE.clear()
-        _META_CACHE[key[0]] = (key, meta)
+        _meta_store(attention_mask, meta)
         return meta
 
     # ------------------------------------------------------------------ forward
