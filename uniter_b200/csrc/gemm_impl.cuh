@@ -2,13 +2,13 @@
 //
 //   D[M,N] = epilogue( sum_k A[m,k] * B[n,k] ),  16-bit operands, fp32 accumulation in TMEM.
 //
-// One persistent CTA per SM, 12 warps with fixed roles:
+// One persistent CTA per SM, 12 or 16 warps with fixed roles:
 //   warp 0      TMA producer   — one lane streams 128xBK A tiles and BNxBK B tiles into a
 //                                128B-swizzled smem ring (mbarrier full/empty pairs)
 //   warp 1      MMA issuer     — one lane issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage,
 //                                tcgen05.commit releases smem slots and publishes accumulators
 //   warp 2      TMEM allocator — 2 x BN fp32 columns (double-buffered accumulator)
-//   warps 4-11  epilogue       — two warps per TMEM lane quarter (each takes half of the BN
+//   warps 4-..  epilogue       — 2 (3 for BN = 192) warps per TMEM lane quarter (each takes a share of the BN
 //                                columns): tcgen05.ld 32 lanes x 32 columns, bias / dropout /
 //                                residual / GELU / dGELU / accumulate / column-sum, 16-byte stores
 // The mainloop of tile i+1 overlaps the epilogue of tile i through the two TMEM buffers.
@@ -39,8 +39,14 @@
 namespace ub {
 
 constexpr int A_TILE_BYTES = BM * BK * 2;
-constexpr int EPI_WARPS = 8;                        // 2 per TMEM lane quarter / SM sub-partition
-constexpr int GEMM_THREADS = 128 + 32 * EPI_WARPS;  // 384
+// Epilogue warps: a warp can only read the TMEM lane quarter (warp % 4), so more warps means
+// splitting the BN columns further.  ncu on the K = 768 GEMMs (3 tiles per CTA or one fully exposed
+// tile) showed the epilogue issue-bound with 2 warps per scheduler at 46 % issue utilisation; the
+// 192-wide tile (6 column blocks) is split 3 ways -> 12 epilogue warps, 3 per scheduler.  (256-wide
+// tiles stay at 2: their 4-stage ring leaves no shared memory for more transpose buffers.)
+constexpr int epi_split(int bn) { return bn == 192 ? 3 : 2; }
+constexpr int epi_warps(int bn) { return 4 * epi_split(bn); }
+constexpr int gemm_threads(int bn) { return 128 + 32 * epi_warps(bn); }   // 384 or 512
 
 template <int BN, int kCtas>
 struct GemmCfg {
@@ -50,6 +56,8 @@ struct GemmCfg {
   // two accumulators of BN fp32 columns; allocations must be a power of two >= 32
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512);
   static constexpr int BAR_BYTES = 256;
+  static constexpr int EPI_WARPS = epi_warps(BN);
+  static constexpr int THREADS = gemm_threads(BN);
   // per epilogue warp: 32 x 33 fp32 transpose buffer (lane == row  ->  4 lanes per row)
   static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * 33 * 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES + 1024;  // + align slack
@@ -119,7 +127,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmParams& p, uint32_t t_ac
                                               float* stage, uint64_t* empty_bar_local,
                                               uint32_t empty_bar_cluster, bool remote_arrive) {
   using T16 = typename Elem<kBF16>::T;
-  constexpr int CHUNKS = BN / 32 / 2;
+  constexpr int CHUNKS = BN / 32 / epi_split(BN);
   const EpiMask<EPI, kBF16> E(p.epilogue);
   const int sub_r = lane >> 2;        // row inside an 8-row group
   const int cg = (lane & 3) * 8;      // first of this lane's 8 columns inside the 32-column block
@@ -281,7 +289,7 @@ __device__ __forceinline__ DropoutRng make_rng(const GemmParams& p) {
 
 // =================================================================================== 1-SM kernel
 template <int BN, bool A_MN, bool B_MN, bool kBF16, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(BN), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmParams p) {
   using Cfg = GemmCfg<BN, 1>;
@@ -316,7 +324,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[a], Cfg::EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -409,7 +417,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp >= 4) {
     // ===================================================================== epilogue (8 warps)
     const int quarter = warp & 3;         // TMEM lanes [32*quarter, 32*quarter+32)
-    const int chalf = (warp - 4) >> 2;    // which half of the BN columns this warp handles
+    const int chalf = (warp - 4) >> 2;    // which 1/epi_split(BN) of the BN columns this warp handles
     const DropoutRng rng = make_rng(p);
     float* epi_stage = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES) +
                        (warp - 4) * (32 * 33);
@@ -427,7 +435,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       epilogue_warp<EPI, BN, kBF16>(p, t_acc, m0 + quarter * 32, n0, chalf, lane, rng, epi_stage,
                                     &tmem_empty_bar[acc], 0u, false);
       if (warp == 4 && lane == 0) UB_TRACE(unit == static_cast<int>(blockIdx.x) ? 7 : 9);
-      if (warp == 11 && lane == 0) UB_TRACE(10);
+      if (warp == 3 + Cfg::EPI_WARPS && lane == 0) UB_TRACE(10);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -460,7 +468,7 @@ __device__ __forceinline__ int group_of_tile(const GroupedParams& g, int tile) {
 }
 
 template <int BN, bool kBF16, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(BN), 1)
 gemm_group_kernel(const __grid_constant__ TmPack tm, const GroupedParams g) {
   using Cfg = GemmCfg<BN, 1>;
   extern __shared__ uint8_t smem_raw[];
@@ -483,7 +491,7 @@ gemm_group_kernel(const __grid_constant__ TmPack tm, const GroupedParams g) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], EPI_WARPS);
+      mbar_init(&tmem_empty_bar[a], Cfg::EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -594,7 +602,7 @@ gemm_group_kernel(const __grid_constant__ TmPack tm, const GroupedParams g) {
 // =================================================================================== 2-SM kernel
 // CTA pair (cluster of 2): output tile 256 x BN.  rank 0 = leader (issues the MMAs).
 template <int BN, bool A_MN, bool B_MN, bool kBF16, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(BN), 1)
 gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmParams p) {
   using Cfg = GemmCfg<BN, 2>;
@@ -627,7 +635,7 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 2 * EPI_WARPS);  // epilogue warps of BOTH CTAs (leader's copy)
+      mbar_init(&tmem_empty_bar[a], 2 * Cfg::EPI_WARPS);  // epilogue warps of BOTH CTAs (leader's copy)
     }
     fence_barrier_init();
   }
@@ -755,7 +763,7 @@ static int launch_gemm(const GemmParams& p, const CUtensorMap& tmA, const CUtens
   }
   {
     ProfScope ps(stream);
-    UB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, kCluster,
+    UB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, kCluster,
                              tmA, tmB, p));
   }
   return 0;
@@ -824,7 +832,7 @@ int gemm_group_launch(const TmPack& tm, const GroupedParams& g, int grid, cudaSt
     configured[ci] = true;
   }
   ProfScope ps(stream);
-  UB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, 1, tm, g));
+  UB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, 1, tm, g));
   return 0;
 }
 

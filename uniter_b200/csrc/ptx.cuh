@@ -331,14 +331,24 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Standard-normal CDF Phi(x) through erf(|x|/sqrt2) = 1 - poly(t) * exp(-x^2/2),
 // t = 1/(1 + p|x|/sqrt2)  (Abramowitz & Stegun 7.1.26, |abs err| <= 1.5e-7 — far below the
 // 16-bit output rounding).  `ex` returns exp(-x^2/2), shared with the pdf in the derivative.
-// ~12 instructions instead of erff's ~40: the GELU / dGELU GEMM epilogues were ALU-bound.
+// The reciprocal and the exponential are the bare MUFU approximations (rcp.approx.ftz on an
+// argument >= 1, ex2.approx.ftz on x^2 * -log2(e)/2): ncu on the FFN1 GEMM showed 39 issued
+// instructions per output element with __fdividef / __expf — their range-handling FSETP / FMUL /
+// branch sequences — in an epilogue that is issue-bound (2 warps per scheduler, 46 % issue
+// utilisation, tensor pipe 30 % active).
 __device__ __forceinline__ float normal_cdf(float x, float& ex) {
   const float ax = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  ex = __expf(-ax * ax);
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
+  ex = ex2_approx((x * x) * -0.72134752044448170368f);     // exp(-x^2 / 2)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
