@@ -378,6 +378,28 @@ def main():
                     "step_frac_of_peak": round(flops_step / (ms_step * 1e-3) / 1e12 / pk["tflops"], 4),
                     "kernel_time_share_of_step": round(gemm_ms / ms_step, 3)}
 
+    # ---- informational: the same step followed by the fused clip + AdamW update.
+    # NOT part of `value` (BASELINE.json's metric is encoder fwd+bwd); reported beside it.
+    train_step = None
+    if not args.no_profile:
+        from uniter_b200.optim import FusedAdamW
+        decay = [p for n, p in model.named_parameters() if not any(k in n for k in ("bias", "LayerNorm.bias", "LayerNorm.weight"))]
+        nodecay = [p for n, p in model.named_parameters() if any(k in n for k in ("bias", "LayerNorm.bias", "LayerNorm.weight"))]
+        opt = FusedAdamW([{"params": decay, "weight_decay": 0.01}, {"params": nodecay, "weight_decay": 0.0}],
+                         lr=1e-6, betas=(0.9, 0.98))
+
+        def opt_step(i):
+            step(resident)
+            opt.step(max_grad_norm=2.0)
+
+        for i in range(3):
+            opt_step(i)
+        nst = max(5, args.steps // 2)
+        ms_opt = timed(opt_step, nst) / nst
+        train_step = {"ms_per_step": round(ms_opt, 4), "samples_per_s": round(C2["B"] * world / (ms_opt * 1e-3), 1),
+                      "includes": "fwd + bwd%s + global-norm clip + fused multi-tensor AdamW (fp32 masters)"
+                                  % (" + allreduce" if world > 1 else "")}
+
     # ---- CPU baseline (rank 0, N == 1 only): oracle port on the host cores, bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -402,7 +424,8 @@ def main():
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(cpu_enqueue_ms, 3),
             "algorithmic_tflops_per_step": round(flops_step / 1e12, 4),
             "achieved_tflops": round(flops_step / (ms_step * 1e-3) / 1e12, 1),
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "breakdown": breakdown,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "train_step": train_step,
+            "breakdown": breakdown,
         }
         print(json.dumps(line), file=real_out, flush=True)
     if world > 1:

@@ -172,3 +172,29 @@ def test_embedding_table_gradient_kernels_vs_torch():
         F = pos_feat[img_src.clamp(min=0).long()].to(dtype).float() * (kind == 1).unsqueeze(1)
         ref_wp = du.float().t() @ F
         assert (d_wpos - ref_wp).abs().max().item() <= 2e-3 * max(1.0, ref_wp.abs().max().item())
+
+
+def test_collate_prefetch_pipeline_matches_plain_batches():
+    """Host batching -> pinned side-stream H2D -> registered lengths (no device sync in forward)
+    gives the same losses as feeding the same collated batch without any registration."""
+    from tests.golden.make_goldens import batching_samples
+    from uniter_b200 import batching
+    from uniter_b200.heads import UniterForMLM
+    torch.manual_seed(1)
+    mod = UniterForMLM(util.tiny_config(), 16).to("cuda", torch.float16).eval()
+    samples = batching_samples(41, 24, True)
+    lens = [s[3].numel() for s in samples]
+    import random
+    sampler = batching.TokenBucketSampler(lens, bucket_size=16, batch_size=160, rng=random.Random(0))
+    host_batches = [batching.mlm_collate([samples[i] for i in ids]) for ids in iter(sampler)]
+    assert len(host_batches) >= 2 and sum(len(b["txt_lens"]) for b in host_batches) == 24
+    got = []
+    with torch.no_grad():
+        for batch in batching.DevicePrefetcher(host_batches):
+            assert batch["attn_masks"].is_cuda
+            got.append(mod(batch).float().cpu())
+        for hb, g in zip(host_batches, got):
+            plain = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in hb.items()
+                     if k not in ("mlm_index", "mlm_targets")}
+            ref = mod(plain).float().cpu()
+            assert torch.equal(ref, g)
