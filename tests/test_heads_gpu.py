@@ -197,4 +197,4 @@ def test_collate_prefetch_pipeline_matches_plain_batches():
             plain = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in hb.items()
                      if k not in ("mlm_index", "mlm_targets")}
             ref = mod(plain).float().cpu()
-            assert torch.equal(ref, g)
+            assert ref.shape == g.shape and torch.allclose(ref, g, atol=1e-3, rtol=0)
