@@ -156,6 +156,8 @@ typedef struct {
   const void* dctx;           /* bwd: [T, H] */
   void* dqkv;                 /* bwd: [T, 3H] */
   void* workspace;            /* bwd: fp32 dQ accumulator or NULL */
+  float* dbias;               /* bwd, optional: [3H] fp32, += column sums of dqkv = gradient of the
+                                 stacked query|key|value biases (fused; saves a pass over dqkv) */
 } ub200_attn_args;
 
 int ub200_attn_fwd(const ub200_attn_args* args, ub200_stream_t stream);

@@ -47,8 +47,13 @@ def test_attention_fwd_bwd(dtype, tol, lens, heads):
     assert err <= tol * max(1.0, ref.abs().max().item()), "fwd err %.3e" % err
     dctx = torch.randn(T, H, device="cuda").to(dtype)
     ref.backward(dctx.float())
-    dqkv = ops.attn_bwd(qkv, ctx, lse, dctx, cu, max(lens), heads)
+    dbias = torch.full((3 * H,), 0.5, device="cuda")       # accumulated into: starts non-zero
+    dqkv = ops.attn_bwd(qkv, ctx, lse, dctx, cu, max(lens), heads, dbias=dbias)
     gref = q32.grad
+    # fused QKV bias gradient = column sums of dqkv over the valid rows only
+    bref = gref.sum(0) + 0.5
+    eb = (dbias - bref).abs().max().item()
+    assert eb <= 2 * tol * max(1.0, gref.abs().sum(0).max().item()), "dbias err %.3e (lens=%s)" % (eb, lens)
     for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
         e = (dqkv[:, sl].float() - gref[:, sl]).abs().max().item()
         lim = 2 * tol * max(1.0, gref[:, sl].abs().max().item())

@@ -38,7 +38,7 @@ class AttnArgs(C.Structure):
         ("batch", C.c_int32), ("total_tokens", C.c_int32), ("max_seqlen", C.c_int32),
         ("hidden", C.c_int32), ("num_heads", C.c_int32), ("dtype", C.c_int32),
         ("dropout_p", C.c_float), ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64),
-        ("dctx", C.c_void_p), ("dqkv", C.c_void_p), ("workspace", C.c_void_p),
+        ("dctx", C.c_void_p), ("dqkv", C.c_void_p), ("workspace", C.c_void_p), ("dbias", C.c_void_p),
     ]
 
 

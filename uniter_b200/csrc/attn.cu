@@ -43,7 +43,29 @@ struct AttnParams {
   // backward only
   const void* dctx;        // [T, H]
   void* dqkv;              // [T, 3H]
+  float* dbias;            // [3H] fp32 column sums of dqkv (QKV bias gradient), accumulated; or NULL
 };
+
+// Column sums over the 32 rows (= lanes) of a warp of a 32-column register block: a butterfly in
+// which every step halves the number of live columns per lane (16+8+4+2+1 = 31 shuffles); lane l
+// ends up with the total of column l and adds it to dst[l].  All 32 lanes must call it.
+__device__ __forceinline__ void warp_colsum32_atomic(const uint32_t (&r)[32], bool valid, float* dst,
+                                                     int lane) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = valid ? __uint_as_float(r[i]) : 0.f;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  atomicAdd(dst + lane, v[0]);
+}
 
 // element index used to key the attention-probability dropout mask
 __device__ __forceinline__ uint64_t attn_drop_group(int bh, int q, int key8) {
@@ -514,6 +536,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       uint32_t r[32];
       tmem_ld32(tdQ + lane_off + cc * 32, r);
       tmem_ld_wait();
+      if (p.dbias)   // query-bias gradient: this key block's share of colsum(dQ) for `head`
+        warp_colsum32_atomic(r, q_ok, p.dbias + head * ATT_D + cc * 32, tid & 31);
       if (q_ok) {
         if (nkv == 1) {
           T16* out = reinterpret_cast<T16*>(p.dqkv) + static_cast<size_t>(seq0 + qrow) * (3 * p.H) +
@@ -555,6 +579,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         uint32_t r[32];
         tmem_ld32((which ? tdV : tdK) + lane_off + cc * 32, r);
         tmem_ld_wait();
+        if (p.dbias)   // key / value bias gradients
+          warp_colsum32_atomic(r, k_ok, p.dbias + (which ? 2 : 1) * p.H + head * ATT_D + cc * 32, tid & 31);
         if (k_ok) {
           T16* out = (which ? outv : outk) + cc * 32;
 #pragma unroll
@@ -700,7 +726,7 @@ extern "C" int ub200_attn_bwd(const ub200_attn_args* args, ub200_stream_t stream
   AttnParams p{};
   p.cu_seqlens = a.cu_seqlens;
   p.H = a.hidden; p.nheads = a.num_heads; p.T = a.total_tokens;
-  p.ctx = a.ctx; p.lse = a.lse; p.dctx = a.dctx; p.dqkv = a.dqkv;
+  p.ctx = a.ctx; p.lse = a.lse; p.dctx = a.dctx; p.dqkv = a.dqkv; p.dbias = a.dbias;
   p.scale = 0.125f;
   if (a.dropout_p > 0.f) {
     uint32_t thr = static_cast<uint32_t>(a.dropout_p * 65536.0f + 0.5f);

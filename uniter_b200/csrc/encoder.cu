@@ -298,14 +298,10 @@ extern "C" int ub200_encoder_bwd(const ub200_encoder_desc* d, const ub200_layer_
     at.dropout_p = d->attn_dropout_p; at.rng_seed = d->rng_seed;
     at.rng_stream = rng_stream_of(d, l, SITE_ATTN_PROBS);
     at.dctx = sc + S.bufC; at.dqkv = sc + S.dqkv; at.workspace = attn_ws ? sc + S.attn_ws : nullptr;
+    at.dbias = gr.small + SG.dbqkv;   // dbqkv = colsum(dqkv), fused into the attention backward
     {
       ProfTag _t(16);
       UB_TRY(ub200_attn_bwd(&at, stream));
-    }
-    // ---- dbqkv = colsum(dqkv)
-    {
-      ProfTag _t(17);
-      UB_TRY(ub200_colsum(sc + S.dqkv, gr.small + SG.dbqkv, T, 3 * H, 3 * H, d->dtype, stream));
     }
     // ---- dx = dqkv Wqkv + ds1  -> gradient wrt the layer input
     g = gemm_base(d);

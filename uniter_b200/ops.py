@@ -98,7 +98,7 @@ def attn_fwd(qkv, cu_seqlens, max_seqlen, num_heads, dropout_p=0.0, rng_seed=0, 
 
 
 def attn_bwd(qkv, ctx, lse, dctx, cu_seqlens, max_seqlen, num_heads, dropout_p=0.0, rng_seed=0,
-             rng_stream=0):
+             rng_stream=0, dbias=None):
     lib = _lib.load()
     T, H3 = qkv.shape
     H = H3 // 3
@@ -111,7 +111,7 @@ def attn_bwd(qkv, ctx, lse, dctx, cu_seqlens, max_seqlen, num_heads, dropout_p=0
                       dtype=_lib.dtype_code(qkv.dtype), dropout_p=float(dropout_p),
                       rng_seed=int(rng_seed), rng_stream=int(rng_stream),
                       dctx=dctx.data_ptr(), dqkv=dqkv.data_ptr(),
-                      workspace=ws.data_ptr() if ws_bytes else None)
+                      workspace=ws.data_ptr() if ws_bytes else None, dbias=_lib.ptr(dbias))
     _lib.check(lib.ub200_attn_bwd(C.byref(a), _lib.current_stream()))
     return dqkv
 
