@@ -215,3 +215,24 @@ def test_reference_heads_accept_the_drop_in_model():
     finally:
         rvqa.UniterModel = orig
         rpre.UniterModel = orig
+
+
+def test_prefix_pack_bookkeeping_matches_mask_derived_indices():
+    """Host-side packing metadata (no device reads) == what the mask itself implies."""
+    from uniter_b200.model import _prefix_pack_host
+    for lens, L in (([56, 44], 56), ([1], 1), ([3, 7, 2, 7], 9), ([5] * 64, 72), ([0, 4, 0], 4)):
+        B, T = len(lens), sum(lens)
+        mask = torch.zeros(B, L, dtype=torch.long)
+        for b, s in enumerate(lens):
+            mask[b, :s] = 1
+        host, (o_cu, o_pack, o_unpack) = _prefix_pack_host(lens, L)
+        assert host.dtype == torch.int32 and o_pack % 4 == 0 and o_unpack % 4 == 0
+        cu = host[o_cu:o_cu + B + 1]
+        pack = host[o_pack:o_pack + T]
+        unpack = host[o_unpack:o_unpack + B * L]
+        assert cu.tolist() == [0] + torch.tensor(lens).cumsum(0).tolist()
+        want_pack = mask.reshape(-1).nonzero().squeeze(1).to(torch.int32)
+        assert torch.equal(pack, want_pack)
+        want_unpack = torch.full((B * L,), -1, dtype=torch.int32)
+        want_unpack[want_pack.long()] = torch.arange(T, dtype=torch.int32)
+        assert torch.equal(unpack, want_unpack)

@@ -342,6 +342,28 @@ def _meta_store(t, meta):
     _META_CACHE[id(t)] = (weakref.ref(t), _meta_key(t), meta)
 
 
+def _prefix_pack_host(lens, L):
+    """Packing bookkeeping of a batch of PREFIX masks ([1]*S_b + [0]*(L-S_b)) from the host-known
+    lengths: one int32 buffer holding cu_seqlens [B+1], pack_idx [T] (packed row -> b*L+j) and
+    unpack_idx [B*L] (b*L+j -> packed row, -1 at masked positions); sections start on 16-byte
+    boundaries.  Returns (buffer, (offset_cu, offset_pack, offset_unpack))."""
+    B = len(lens)
+    lens_t = torch.tensor(lens, dtype=torch.int64)
+    T = int(lens_t.sum()) if B else 0
+    cu_t = torch.zeros(B + 1, dtype=torch.int64)
+    if B:
+        torch.cumsum(lens_t, 0, out=cu_t[1:])
+    row_b = torch.repeat_interleave(torch.arange(B), lens_t)
+    pack_h = torch.arange(T) - cu_t[row_b] + row_b * L
+    o_pack = (B + 1 + 3) // 4 * 4
+    o_unpack = o_pack + (T + 3) // 4 * 4
+    host = torch.full((o_unpack + B * L,), -1, dtype=torch.int32)
+    host[:B + 1] = cu_t.to(torch.int32)
+    host[o_pack:o_pack + T] = pack_h.to(torch.int32)
+    host[o_unpack + pack_h] = torch.arange(T, dtype=torch.int32)
+    return host, (0, o_pack, o_unpack)
+
+
 def register_lengths(attention_mask_dev, lens_host, prefix=False):
     """Tell the model the per-sample valid lengths of a device attention mask that the host
     already knows (the loader computed them before the H2D copy), so forward() does not have to
@@ -832,17 +854,20 @@ class UniterModel(UniterPreTrainedModel):
         dev = attention_mask.device
         registered = hit is not None
         if registered and hit.get("prefix"):
-            # prefix masks with host-known lengths: everything from arithmetic, no device reads
+            # prefix masks with host-known lengths: the whole bookkeeping (cu_seqlens, pack and
+            # unpack indices) is integer arithmetic done on the HOST and shipped in one small H2D
+            # copy — no device reads, no index kernels
             lens_h = hit["lens_host"]
             T = int(sum(lens_h))
-            cu_h = [0]
-            for v in lens_h:
-                cu_h.append(cu_h[-1] + v)
-            meta_h = torch.tensor([cu_h, lens_h + [0]], dtype=torch.int64)
-            meta_d = meta_h.to(dev, non_blocking=True)
-            cu = meta_d[0].to(torch.int32)
-            row_b = torch.repeat_interleave(torch.arange(B, device=dev), meta_d[1, :B], output_size=T)
-            pack_idx = (torch.arange(T, device=dev) - meta_d[0][row_b] + row_b * L).to(torch.int32)
+            host, (o_cu, o_pack, o_unpack) = _prefix_pack_host(lens_h, L)
+            devbuf = host.to(dev, non_blocking=True)
+            cu = devbuf[o_cu:o_cu + B + 1]
+            pack_idx = devbuf[o_pack:o_pack + T]
+            unpack_idx = devbuf[o_unpack:o_unpack + B * L]
+            meta = dict(batch=B, L=L, total=T, max_seqlen=max(lens_h) if lens_h else 0,
+                        cu_seqlens=cu, pack_idx=pack_idx, unpack_idx=unpack_idx, lens_host=lens_h)
+            _meta_store(attention_mask, meta)
+            return meta
         else:
             am = attention_mask != 0
             lens = am.sum(1)
