@@ -183,3 +183,39 @@ def ptr(t):
 def current_stream():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+class PinnedRing(object):
+    """Rotating pinned host staging buffers for small per-step H2D copies (packing metadata,
+    optimizer segment tables).  A copy from PAGEABLE memory makes the host wait until the stream
+    has drained, i.e. it costs a full synchronisation per step; from pinned memory it is just
+    another asynchronous stream operation.  A slot is reused only after the copy that last read it
+    has completed (event), which in steady state is always already true."""
+
+    def __init__(self, slots=8):
+        self.slots = [None] * slots
+        self.events = [None] * slots
+        self.i = 0
+
+    def upload(self, host_tensor, device):
+        """Async copy of a contiguous CPU tensor to `device` through a pinned slot."""
+        import torch
+        nbytes = host_tensor.numel() * host_tensor.element_size()
+        k = self.i
+        self.i = (self.i + 1) % len(self.slots)
+        if self.events[k] is not None:
+            self.events[k].synchronize()
+        buf = self.slots[k]
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8).pin_memory()
+            self.slots[k] = buf
+        stage = buf[:nbytes].view(host_tensor.dtype)
+        stage.copy_(host_tensor.reshape(-1))
+        dev = torch.empty(host_tensor.numel(), dtype=host_tensor.dtype, device=device)
+        dev.copy_(stage, non_blocking=True)
+        ev = self.events[k]
+        if ev is None:
+            ev = torch.cuda.Event()
+            self.events[k] = ev
+        ev.record(torch.cuda.current_stream(device))
+        return dev

@@ -317,6 +317,7 @@ def _bind():
 
 _rng_offset = [0]
 _META_CACHE = {}
+_META_RING = _lib.PinnedRing(8)
 
 
 def _meta_key(t):
@@ -860,7 +861,7 @@ class UniterModel(UniterPreTrainedModel):
             lens_h = hit["lens_host"]
             T = int(sum(lens_h))
             host, (o_cu, o_pack, o_unpack) = _prefix_pack_host(lens_h, L)
-            devbuf = host.to(dev, non_blocking=True)
+            devbuf = _META_RING.upload(host, dev)
             cu = devbuf[o_cu:o_cu + B + 1]
             pack_idx = devbuf[o_pack:o_pack + T]
             unpack_idx = devbuf[o_unpack:o_unpack + B * L]

@@ -72,6 +72,7 @@ class FusedAdamW(object):
         self._dev_tables = None  # (segs uint8 tensor, blk_start int32 tensor) on the device
         self._sumsq = None
         self.last_sumsq = None   # device scalar: sum of squares of the (scaled) gradients
+        self._ring = _lib.PinnedRing(8)
 
     # ------------------------------------------------------------------ state
     def _init_state(self, p):
@@ -170,8 +171,9 @@ class FusedAdamW(object):
         arr = (_lib.AdamSegment * nseg)(*segs)
         seg_bytes = C.sizeof(arr)
         host = torch.frombuffer(bytearray(C.string_at(C.addressof(arr), seg_bytes)), dtype=torch.uint8)
-        segs_dev = host.to(dev, non_blocking=False)
-        starts_dev = torch.tensor(starts, dtype=torch.int32).to(dev)
+        # pinned staging: a pageable H2D copy here would drain the stream (a sync per step)
+        segs_dev = self._ring.upload(host, dev)
+        starts_dev = self._ring.upload(torch.tensor(starts, dtype=torch.int32), dev)
         stream = _lib.current_stream()
         sumsq_ptr = None
         if max_grad_norm is not None and max_grad_norm > 0:
