@@ -21,6 +21,7 @@ import logging
 import math
 import weakref
 
+import numpy as np
 import torch
 from torch import nn
 
@@ -349,19 +350,19 @@ def _prefix_pack_host(lens, L):
     unpack_idx [B*L] (b*L+j -> packed row, -1 at masked positions); sections start on 16-byte
     boundaries.  Returns (buffer, (offset_cu, offset_pack, offset_unpack))."""
     B = len(lens)
-    lens_t = torch.tensor(lens, dtype=torch.int64)
-    T = int(lens_t.sum()) if B else 0
-    cu_t = torch.zeros(B + 1, dtype=torch.int64)
-    if B:
-        torch.cumsum(lens_t, 0, out=cu_t[1:])
-    row_b = torch.repeat_interleave(torch.arange(B), lens_t)
-    pack_h = torch.arange(T) - cu_t[row_b] + row_b * L
+    lens_a = np.asarray(lens, dtype=np.int64).reshape(B)
+    cu = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum(lens_a, out=cu[1:])
+    T = int(cu[-1])
+    row_b = np.repeat(np.arange(B, dtype=np.int64), lens_a)     # (torch.repeat_interleave on CPU
+    pack = np.arange(T, dtype=np.int64) - cu[row_b] + row_b * L  #  costs ~20 ms here; numpy ~20 us)
     o_pack = (B + 1 + 3) // 4 * 4
     o_unpack = o_pack + (T + 3) // 4 * 4
-    host = torch.full((o_unpack + B * L,), -1, dtype=torch.int32)
-    host[:B + 1] = cu_t.to(torch.int32)
-    host[o_pack:o_pack + T] = pack_h.to(torch.int32)
-    host[o_unpack + pack_h] = torch.arange(T, dtype=torch.int32)
+    buf = np.full(o_unpack + B * L, -1, dtype=np.int32)
+    buf[:B + 1] = cu
+    buf[o_pack:o_pack + T] = pack
+    buf[o_unpack + pack] = np.arange(T, dtype=np.int32)
+    host = torch.from_numpy(buf)
     return host, (0, o_pack, o_unpack)
 
 
