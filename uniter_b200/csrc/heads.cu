@@ -183,9 +183,25 @@ sumsq_kernel(const ub200_adam_segment* __restrict__ segs, const int* __restrict_
   const ub200_adam_segment sg = segs[s];
   const long long base = static_cast<long long>(blockIdx.x - blk_start[s]) * ADAM_CHUNK;
   float acc = 0.f;
-  for (int j = threadIdx.x; j < ADAM_CHUNK; j += 256) {
-    const long long i = base + j;
-    if (i < sg.n) { const float g = grad_of(sg, i); acc = fmaf(g, g, acc); }
+  if (sg.grad_dtype != UB200_F32 && sg.n % 8 == 0 && (reinterpret_cast<uintptr_t>(sg.grad) & 15) == 0) {
+    const bool bf = sg.grad_dtype == UB200_BF16;
+    for (int j = threadIdx.x * 8; j < ADAM_CHUNK; j += 2048) {
+      const long long i = base + j;
+      if (i >= sg.n) break;
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(sg.grad) + i));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = bf ? Elem<true>::unpack(w[q]) : Elem<false>::unpack(w[q]);
+        acc = fmaf(f.x, f.x, acc);
+        acc = fmaf(f.y, f.y, acc);
+      }
+    }
+  } else {
+    for (int j = threadIdx.x; j < ADAM_CHUNK; j += 256) {
+      const long long i = base + j;
+      if (i < sg.n) { const float g = grad_of(sg, i); acc = fmaf(g, g, acc); }
+    }
   }
   acc = block_sum(acc, red);
   if (threadIdx.x == 0 && acc != 0.f) atomicAdd(out, acc);
@@ -213,16 +229,51 @@ adamw_kernel(const ub200_adam_segment* __restrict__ segs, const int* __restrict_
     const float coef = h.max_norm / (total + 1e-6f);
     if (coef < 1.f) gmul *= coef;
   }
-  for (int j = threadIdx.x; j < ADAM_CHUNK; j += 256) {
-    const long long i = base + j;
-    if (i >= sg.n) break;
-    const float g = grad_of(sg, i) * gmul;
-    float m = sg.exp_avg[i], v = sg.exp_avg_sq[i], p = sg.master[i];
+  auto update = [&](float g, float& m, float& v, float& p) {
+    g *= gmul;
     m = m * h.beta1 + (1.0f - h.beta1) * g;              // optim/adamw.py:77
     v = v * h.beta2 + (1.0f - h.beta2) * g * g;          // :78
     const float denom = sqrtf(v) + h.eps;                // :79
     p = p - sg.step_size * (m / denom);                  // :81-88 (step_size bias-corrected on host)
     if (sg.lr_wd > 0.f) p = p - sg.lr_wd * p;            // :99-100 decoupled decay AFTER the update
+  };
+  // vector path: 4 elements per thread (16-byte fp32 accesses, 8-byte 16-bit accesses) when the
+  // segment is a 16-bit parameter with a 16-bit gradient of the same type and everything is aligned
+  const bool vec = (sg.n % 4 == 0) && sg.model != nullptr && sg.grad_dtype == sg.model_dtype &&
+                   sg.grad_dtype != UB200_F32 &&
+                   ((reinterpret_cast<uintptr_t>(sg.master) | reinterpret_cast<uintptr_t>(sg.exp_avg) |
+                     reinterpret_cast<uintptr_t>(sg.exp_avg_sq)) & 15) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(sg.grad) | reinterpret_cast<uintptr_t>(sg.model)) & 7) == 0;
+  if (vec) {
+    const bool bf = sg.grad_dtype == UB200_BF16;
+    for (int j = threadIdx.x * 4; j < ADAM_CHUNK; j += 1024) {
+      const long long i = base + j;
+      if (i >= sg.n) break;
+      const uint2 graw = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(sg.grad) + i);
+      float4 m4 = *reinterpret_cast<const float4*>(sg.exp_avg + i);
+      float4 v4 = *reinterpret_cast<const float4*>(sg.exp_avg_sq + i);
+      float4 p4 = *reinterpret_cast<const float4*>(sg.master + i);
+      const float2 g01 = bf ? Elem<true>::unpack(graw.x) : Elem<false>::unpack(graw.x);
+      const float2 g23 = bf ? Elem<true>::unpack(graw.y) : Elem<false>::unpack(graw.y);
+      update(g01.x, m4.x, v4.x, p4.x);
+      update(g01.y, m4.y, v4.y, p4.y);
+      update(g23.x, m4.z, v4.z, p4.z);
+      update(g23.y, m4.w, v4.w, p4.w);
+      *reinterpret_cast<float4*>(sg.exp_avg + i) = m4;
+      *reinterpret_cast<float4*>(sg.exp_avg_sq + i) = v4;
+      *reinterpret_cast<float4*>(sg.master + i) = p4;
+      uint2 o;
+      o.x = bf ? Elem<true>::pack(p4.x, p4.y) : Elem<false>::pack(p4.x, p4.y);
+      o.y = bf ? Elem<true>::pack(p4.z, p4.w) : Elem<false>::pack(p4.z, p4.w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(sg.model) + i) = o;
+    }
+    return;
+  }
+  for (int j = threadIdx.x; j < ADAM_CHUNK; j += 256) {
+    const long long i = base + j;
+    if (i >= sg.n) break;
+    float m = sg.exp_avg[i], v = sg.exp_avg_sq[i], p = sg.master[i];
+    update(grad_of(sg, i), m, v, p);
     sg.exp_avg[i] = m; sg.exp_avg_sq[i] = v; sg.master[i] = p;
     if (sg.model) {
       if (sg.model_dtype == UB200_BF16) reinterpret_cast<__nv_bfloat16*>(sg.model)[i] = __float2bfloat16_rn(p);
