@@ -358,6 +358,7 @@ def main():
                      for i in range(NT) if cnt_arr[i] > 0}
         gemm_tags = [1, 3, 5, 6, 9, 10, 11, 12, 14, 15, 18, 19]
         gemm_ms = sum(ms_arr[i] for i in gemm_tags) / psteps
+        all_ms = sum(ms_arr[i] for i in range(NT)) / psteps       # every library launch, same (serialised) mode
         gemm_launches = sum(cnt_arr[i] for i in gemm_tags) // psteps
         T = sum(lens0)
         gemm_flops = 3.0 * NL * 24.0 * BASE["H"] ** 2 * T          # dense-projection part of §8d
@@ -376,7 +377,10 @@ def main():
                     "algorithmic_flops_per_step": gemm_flops, "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write)",
                     "traffic_source": traffic_src,
                     "step_frac_of_peak": round(flops_step / (ms_step * 1e-3) / 1e12 / pk["tflops"], 4),
-                    "kernel_time_share_of_step": round(gemm_ms / ms_step, 3)}
+                    "kernel_time_share_of_step": round(gemm_ms / max(all_ms, 1e-9), 3),
+                    "share_basis": "event pass: the 12 GEMM roles / all library launches, both timed launch by "
+                                   "launch (serialised); compare with the ncu launch list in profiles/",
+                    "event_pass_ms_per_step": round(all_ms, 4)}
 
     # ---- informational: the same step followed by the fused clip + AdamW update.
     # NOT part of `value` (BASELINE.json's metric is encoder fwd+bwd); reported beside it.
