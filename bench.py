@@ -289,7 +289,6 @@ def main():
 
     ms_total = timed(timed_step, args.steps)
     cpu_enqueue_ms = cpu_t[0] / args.steps * 1e3   # host time to enqueue one step (no sync inside)
-    clocks = sampler.stop() if rank == 0 else None
     launches = (lib.ub200_launch_count() - launches0) // args.steps
     ms_step = ms_total / args.steps
     value = C2["B"] * world / (ms_step * 1e-3)
@@ -332,6 +331,7 @@ def main():
     for i in range(n_warm):
         e2e_step(i)
     ms_e2e = timed(lambda i: e2e_step(n_warm + i), args.steps) / args.steps
+    clocks = sampler.stop() if rank == 0 else None     # sampled across both timed regions (under load)
     assert all(l == l for l in losses), "NaN loss in the e2e leg"
     e2e_value = C2["B"] * world / (ms_e2e * 1e-3)
 
