@@ -251,6 +251,65 @@ def run_batching(out_path):
     print("wrote", out_path, "%.1f KB" % (os.path.getsize(out_path) / 1024))
 
 
+def hardneg_inputs(sample_from, seed):
+    """A 9-pair hard-negative batch as data/itm.py:270-361 builds it (one text x 9 images, or one
+    image x 9 texts), plus random pair scores."""
+    from uniter_b200.synth import get_gather_index
+    g = torch.Generator().manual_seed(seed)
+    n, D = 9, 16
+    if sample_from == "t":
+        tl = 6
+        input_ids = torch.randint(1000, 2000, (1, tl), generator=g)
+        num_bbs = torch.randint(2, 8, (n,), generator=g).tolist()
+        img_feat = torch.zeros(n, max(num_bbs), D)
+        img_pos = torch.zeros(n, max(num_bbs), 7)
+        for i, nb in enumerate(num_bbs):
+            img_feat[i, :nb] = torch.randn(nb, D, generator=g)
+            img_pos[i, :nb] = torch.rand(nb, 7, generator=g)
+        attn = torch.zeros(n, max(num_bbs) + tl, dtype=torch.long)
+        for i, nb in enumerate(num_bbs):
+            attn[i, :tl + nb] = 1
+        gather = get_gather_index([tl] * n, num_bbs, n, tl, attn.size(1))
+    else:
+        nbb = 5
+        txt_lens = torch.randint(3, 9, (n,), generator=g).tolist()
+        input_ids = torch.zeros(n, max(txt_lens), dtype=torch.long)
+        for i, tl in enumerate(txt_lens):
+            input_ids[i, :tl] = torch.randint(1000, 2000, (tl,), generator=g)
+        img_feat = torch.randn(1, nbb, D, generator=g)
+        img_pos = torch.rand(1, nbb, 7, generator=g)
+        attn = torch.zeros(n, max(txt_lens) + nbb, dtype=torch.long)
+        for i, tl in enumerate(txt_lens):
+            attn[i, :tl + nbb] = 1
+        # data/itm.py:356-361 passes the LAST loop value of tl as max_len (the malformed index)
+        gather = get_gather_index(txt_lens, [nbb] * n, n, txt_lens[-1], attn.size(1))
+    batch = {"input_ids": input_ids, "position_ids": torch.arange(input_ids.size(1)).unsqueeze(0),
+             "img_feat": img_feat, "img_pos_feat": img_pos, "attn_masks": attn, "gather_index": gather}
+    scores = torch.randn(n, 1, generator=g)
+    return batch, scores
+
+
+def run_hardneg(rm, out_path):
+    """Row selection of the reference's UniterForImageTextRetrievalHardNeg._get_hard_batch."""
+    import model.itm as ritm
+    cfg = rm.UniterConfig(**TINY)
+    mod = ritm.UniterForImageTextRetrievalHardNeg(cfg, 16, hard_size=3)
+    rec = {}
+    for sf in ("t", "i"):
+        batch, scores = hardneg_inputs(sf, seed=77)
+        n = batch["attn_masks"].size(0)
+        if sf == "t":
+            batch["input_ids"] = batch["input_ids"].expand(n, -1)
+        else:
+            batch["img_feat"] = batch["img_feat"].expand(n, -1, -1)
+            batch["img_pos_feat"] = batch["img_pos_feat"].expand(n, -1, -1)
+        hb = mod._get_hard_batch(batch, scores, sf)
+        for k, v in hb.items():
+            rec["%s/%s" % (sf, k)] = v.numpy() if torch.is_tensor(v) else np.array(v)
+    np.savez_compressed(out_path, **rec)
+    print("wrote", out_path, "%.1f KB" % (os.path.getsize(out_path) / 1024))
+
+
 def run_adamw(out_path):
     """4 steps of the reference's own AdamW (optim/adamw.py) + clip_grad_norm_ on seeded fp32
     tensors: two param groups (decay 0.01 / 0), a linear-warmup lr per step, gradient clipping at
@@ -315,6 +374,7 @@ def main():
     c1b = synth_batch(2, 0, 0, 0, 0, seed=0, txt_lens=[20, 14], num_bbs=[36, 30])
     run_case(rm, BASE_L1, 2048, c1b, os.path.join(HERE, "c1b.npz"), full_grads=False)
     run_heads(rm, rvqa, rpre, os.path.join(HERE, "heads_tiny.npz"))
+    run_hardneg(rm, os.path.join(HERE, "hardneg.npz"))
     run_adamw(os.path.join(HERE, "adamw.npz"))
     run_batching(os.path.join(HERE, "batching.npz"))
 

@@ -211,3 +211,61 @@ class UniterForImageTextRetrieval(UniterPreTrainedModel):
             pos, neg = scores[:, :1], scores[:, 1:]
             return torch.clamp(self.margin + neg - pos, 0)
         return rank_scores
+
+
+class UniterForImageTextRetrievalHardNeg(UniterForImageTextRetrieval):
+    """model/itm.py:57-147 — in-batch hard-negative mining: score all N candidate pairs of one
+    text (sample_from='t') or one image ('i') without gradients in eval mode, keep the positive
+    (row 0) and the `hard_size` best-scoring negatives, and train on those."""
+
+    def __init__(self, config, img_dim, margin=0.2, hard_size=16):
+        super().__init__(config, img_dim, margin)
+        self.hard_size = hard_size
+
+    def forward(self, batch, sample_from="t", compute_loss=True):
+        n_pairs = batch["attn_masks"].size(0)
+        if sample_from == "t":                       # one text shared by every pair
+            if batch["input_ids"].size(0) == 1:
+                batch["input_ids"] = batch["input_ids"].expand(n_pairs, -1)
+        elif sample_from == "i":                     # one image shared by every pair
+            for key in ("img_feat", "img_pos_feat"):
+                if batch[key].size(0) == 1:
+                    batch[key] = batch[key].expand(n_pairs, -1, -1)
+        else:
+            raise ValueError()
+        if not (self.training and compute_loss):
+            return super().forward(batch, compute_loss)
+        with torch.no_grad():
+            self.eval()
+            scores = super().forward(batch, compute_loss=False)
+            hard_batch = self._get_hard_batch(batch, scores, sample_from)
+            self.train()
+        return super().forward(hard_batch, compute_loss=True)
+
+    def _get_hard_batch(self, batch, scores, sample_from="t"):
+        """Row selection of model/itm.py:92-147 (pure index logic, pinned bit-exactly against the
+        reference in tests/test_heads_optim_cpu.py)."""
+        batch = defaultdict(lambda: None, batch)
+        k = self.hard_size
+        neg = scores.squeeze(-1)[1:].topk(k, sorted=False)[1] + 1          # positive is row 0
+        rows = torch.cat([neg.new_zeros(1), neg])
+        masks = batch["attn_masks"].index_select(0, rows)
+        gather = batch["gather_index"].index_select(0, rows)
+        pos = batch["position_ids"]
+        if pos.size(0) != 1:
+            pos = pos[:k + 1]
+        ids, feat, box = batch["input_ids"], batch["img_feat"], batch["img_pos_feat"]
+        if sample_from == "t":
+            longest = masks.sum(dim=1).max().item()                         # cut to minimum padding
+            n_img = longest - ids.size(1)
+            masks, gather = masks[:, :longest], gather[:, :longest]
+            feat = feat.index_select(0, rows)[:, :n_img, :]
+            box = box.index_select(0, rows)[:, :n_img, :]
+            ids = ids[:k + 1]
+        elif sample_from == "i":
+            ids = ids.index_select(0, rows)
+            feat, box = feat[:k + 1], box[:k + 1]
+        else:
+            raise ValueError()
+        return {"sample_size": k + 1, "input_ids": ids, "position_ids": pos, "img_feat": feat,
+                "img_pos_feat": box, "attn_masks": masks, "gather_index": gather}
