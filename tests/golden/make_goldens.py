@@ -357,6 +357,12 @@ BASE_L1 = dict(vocab_size_or_config_json_file=28996, hidden_size=768, num_hidden
                max_position_embeddings=512, type_vocab_size=2, initializer_range=0.02)
 
 
+LARGE_L1 = dict(vocab_size_or_config_json_file=28996, hidden_size=1024, num_hidden_layers=1,
+                num_attention_heads=16, intermediate_size=4096, hidden_act="gelu",
+                hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1,
+                max_position_embeddings=512, type_vocab_size=2, initializer_range=0.02)
+
+
 def main():
     from uniter_b200.synth import synth_batch
     rm, rvqa, rpre = import_reference()
@@ -373,6 +379,9 @@ def main():
     run_case(rm, BASE_L1, 2048, c1a, os.path.join(HERE, "c1a.npz"), full_grads=False)
     c1b = synth_batch(2, 0, 0, 0, 0, seed=0, txt_lens=[20, 14], num_bbs=[36, 30])
     run_case(rm, BASE_L1, 2048, c1b, os.path.join(HERE, "c1b.npz"), full_grads=False)
+    # UNITER-large geometry (config/uniter-large.json: H 1024, 16 heads, I 4096), 1 layer, ragged
+    lg = synth_batch(2, 0, 0, 0, 0, seed=3, txt_lens=[9, 6], num_bbs=[11, 14])
+    run_case(rm, LARGE_L1, 2048, lg, os.path.join(HERE, "large_l1.npz"), full_grads=False)
     run_heads(rm, rvqa, rpre, os.path.join(HERE, "heads_tiny.npz"))
     run_hardneg(rm, os.path.join(HERE, "hardneg.npz"))
     run_adamw(os.path.join(HERE, "adamw.npz"))

@@ -12,6 +12,15 @@ BASE_L1 = dict(vocab_size=28996, hidden_size=768, num_hidden_layers=1, num_atten
                intermediate_size=3072, max_position_embeddings=512, type_vocab_size=2, img_dim=2048)
 
 
+LARGE_L1 = dict(vocab_size=28996, hidden_size=1024, num_hidden_layers=1, num_attention_heads=16,
+                intermediate_size=4096, max_position_embeddings=512, type_vocab_size=2, img_dim=2048)
+
+
+def large_batch():
+    from uniter_b200.synth import synth_batch
+    return synth_batch(2, 0, 0, 0, 0, seed=3, txt_lens=[9, 6], num_bbs=[11, 14])
+
+
 def load_golden(name):
     return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
 
