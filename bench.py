@@ -38,7 +38,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
-    ap.add_argument("--cpu-sample", type=int, default=8, help="samples in the CPU baseline batch")
+    ap.add_argument("--cpu-sample", type=int, default=64,
+                    help="samples in the CPU arm's batch (64 = the full C2 batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--overlap-chunks", type=int, default=4,
@@ -117,35 +118,10 @@ class ClockSampler:
 
 
 # =============================================================================== CPU (reference) arm
-def cpu_reference_run(args, steps, warmup, sample_B):
-    """oracle port of the reference path on the host cores: fwd+bwd of the MLM loss on the first
-    `sample_B` samples of the C2 batch (fp32, padded layout exactly as the reference computes)."""
-    from oracle import encoder_oracle as orc
-    from uniter_b200.synth import seeded_state, synth_batch, uniter_state_shapes
-    NL = args.layers
-    shapes = {"uniter." + k: v for k, v in uniter_state_shapes(BASE["H"], NL, BASE["I"], BASE["vocab"],
-                                                                BASE["max_pos"], 2, BASE["img_dim"]).items()}
-    shapes.update({"cls.predictions.transform.dense.weight": (BASE["H"], BASE["H"]),
-                   "cls.predictions.transform.dense.bias": (BASE["H"],),
-                   "cls.predictions.transform.LayerNorm.weight": (BASE["H"],),
-                   "cls.predictions.transform.LayerNorm.bias": (BASE["H"],),
-                   "cls.predictions.bias": (BASE["vocab"],)})
-    state = {k: v.requires_grad_(True) for k, v in seeded_state(shapes, seed=0).items()}
-    full = synth_batch(C2["B"], C2["tl"][0], C2["tl"][1], C2["nbb"][0], C2["nbb"][1], C2["seed"],
-                       mlm_prob=C2["mlm_prob"])
-    tl, nb = full["txt_lens"][:sample_B], full["num_bbs"][:sample_B]
-    batch = synth_batch(sample_B, 0, 0, 0, 0, C2["seed"], txt_lens=tl, num_bbs=nb, mlm_prob=C2["mlm_prob"])
-    def one_step():
-        for v in state.values():
-            v.grad = None
-        t0 = time.perf_counter()
-        loss = orc.mlm_forward(state, NL, BASE["heads"], batch).mean()
-        loss.backward()
-        return time.perf_counter() - t0
-
-    # "all the host threads it can use": torch's CPU GEMMs on these small matrices get SLOWER when
-    # oversubscribed (128 threads: 0.2 samples/s vs 8 threads: ~20), so probe upwards and keep
-    # the fastest thread count — that is the honest best case for the CPU arm.
+def _probe_threads(one_step):
+    """"all the host threads it can use": torch's CPU GEMMs on these small matrices get SLOWER when
+    oversubscribed (128 threads: 0.2 samples/s vs 8 threads: ~20), so probe upwards and keep the
+    fastest thread count — the honest best case for the CPU arm."""
     ncpu = os.cpu_count() or 1
     best_t, best_n = None, 1
     for n in [c for c in (4, 8, 16, 32, 64, 128, 256) if c <= ncpu] or [ncpu]:
@@ -156,11 +132,75 @@ def cpu_reference_run(args, steps, warmup, sample_B):
         elif t > 1.5 * best_t:
             break
     torch.set_num_threads(best_n)
+    return best_n
+
+
+def cpu_reference_run(args, steps, warmup, sample_B):
+    """The reference's OWN path on the host cores: `UniterForPretraining.forward(batch, 'mlm')`
+    (model/pretrain.py:107-133 over model/model.py:336-367) fwd+bwd of the mean MLM loss, fp32,
+    train mode (dropout 0.1), on the padded [B, L] rectangle exactly as the reference computes it.
+    Runs the UNMODIFIED reference modules staged in oracle/_ref (kind "reference"); only when they
+    are absent, the clean-room oracle port (kind "port")."""
+    from oracle import ref_loader
+    from uniter_b200.synth import seeded_state, synth_batch
+    NL = args.layers
+    full = synth_batch(C2["B"], C2["tl"][0], C2["tl"][1], C2["nbb"][0], C2["nbb"][1], C2["seed"],
+                       mlm_prob=C2["mlm_prob"])
+    if sample_B >= C2["B"]:
+        sample_B, batch = C2["B"], full
+    else:
+        tl, nb = full["txt_lens"][:sample_B], full["num_bbs"][:sample_B]
+        batch = synth_batch(sample_B, 0, 0, 0, 0, C2["seed"], txt_lens=tl, num_bbs=nb, mlm_prob=C2["mlm_prob"])
+    T = sum(a + b for a, b in zip(batch["txt_lens"], batch["num_bbs"]))
+    kind = ref_loader.kind()
+    if kind == "reference":
+        rm, rpre = ref_loader.load("model.model", "model.pretrain")
+        cfg = rm.UniterConfig(BASE["vocab"], hidden_size=BASE["H"], num_hidden_layers=NL,
+                              num_attention_heads=BASE["heads"], intermediate_size=BASE["I"],
+                              max_position_embeddings=BASE["max_pos"])
+        torch.manual_seed(0)
+        model = rpre.UniterForPretraining(cfg, BASE["img_dim"], 1601).train()
+        ref_batch = {k: v for k, v in batch.items() if torch.is_tensor(v)}
+
+        def one_step():
+            model.zero_grad()
+            t0 = time.perf_counter()
+            loss = model(ref_batch, task="mlm", compute_loss=True).mean()
+            loss.backward()
+            return time.perf_counter() - t0
+    else:
+        from oracle import encoder_oracle as orc
+        from uniter_b200.synth import uniter_state_shapes
+        shapes = {"uniter." + k: v for k, v in uniter_state_shapes(BASE["H"], NL, BASE["I"], BASE["vocab"],
+                                                                    BASE["max_pos"], 2, BASE["img_dim"]).items()}
+        shapes.update({"cls.predictions.transform.dense.weight": (BASE["H"], BASE["H"]),
+                       "cls.predictions.transform.dense.bias": (BASE["H"],),
+                       "cls.predictions.transform.LayerNorm.weight": (BASE["H"],),
+                       "cls.predictions.transform.LayerNorm.bias": (BASE["H"],),
+                       "cls.predictions.bias": (BASE["vocab"],)})
+        state = {k: v.requires_grad_(True) for k, v in seeded_state(shapes, seed=0).items()}
+
+        def one_step():
+            for v in state.values():
+                v.grad = None
+            t0 = time.perf_counter()
+            loss = orc.mlm_forward(state, NL, BASE["heads"], batch).mean()
+            loss.backward()
+            return time.perf_counter() - t0
+
+    best_n = _probe_threads(one_step)
     times = [one_step() for _ in range(warmup + steps)]
     t = sum(times[warmup:]) / max(1, steps)
-    return dict(value=sample_B / t, ms_per_step=t * 1e3, cores=best_n,
-                sample="first %d of the %d C2 samples (T=%d valid tokens), %d timed fwd+bwd steps, fp32"
-                       % (sample_B, C2["B"], sum(a + b for a, b in zip(tl, nb)), steps))
+    what = ("all %d C2 samples" % sample_B) if sample_B == C2["B"] else \
+        ("first %d of the %d C2 samples" % (sample_B, C2["B"]))
+    return dict(value=sample_B / t, ms_per_step=t * 1e3, cores=best_n, host_cores=os.cpu_count() or 1,
+                kind=kind, batch=sample_B,
+                sample="%s (T=%d valid tokens, padded rectangle), %d timed fwd+bwd steps after %d warm-up, "
+                       "fp32, dropout 0.1, %s; %d torch threads (fastest of a 4..%d probe) on %d host cores"
+                       % (what, T, steps, warmup,
+                          "UNMODIFIED reference UniterForPretraining('mlm') from oracle/_ref" if kind == "reference"
+                          else "oracle port (reference sources not staged)",
+                          best_n, os.cpu_count() or 1, os.cpu_count() or 1))
 
 
 # =============================================================================== our arm
@@ -179,16 +219,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_run(args, max(1, min(args.steps, 3)), 1, args.cpu_sample)
+        nst = max(1, min(args.steps, 3))
+        r = cpu_reference_run(args, nst, 1, args.cpu_sample)
+        cb = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "host_cores": r["host_cores"],
+              "kind": r["kind"], "sample": r["sample"]}
         line = {"metric": METRIC, "value": r["value"], "unit": "samples/s", "impl": "reference",
-                "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)), "warmup": 1,
+                "n_gpus": args.gpus, "steps": nst, "warmup": 1,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "C2: UNITER-base %d-layer fwd+bwd + MLM head, CPU port of the "
-                                       "reference path, bounded sample" % args.layers,
-                           "global_batch": args.cpu_sample},
-                "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"],
-                                 "kind": "port", "sample": r["sample"]},
+                "config": {"workload": "C2: UNITER-base %d-layer encoder fwd+bwd + MLM head (15%% text masked), "
+                                       "B=%d, the reference's own CPU path (%s), train mode dropout 0.1"
+                                       % (args.layers, r["batch"], r["kind"]),
+                           "global_batch": r["batch"], "parallelism": "cpu"},
+                "cpu_baseline": cb,
                 "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
         print(json.dumps(line), file=real_out, flush=True)
@@ -412,8 +455,8 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(args, 2, 1, args.cpu_sample)
-        cpu = {"value": round(r["value"], 2), "unit": "samples/s", "cores": r["cores"], "kind": "port",
-               "sample": r["sample"]}
+        cpu = {"value": round(r["value"], 2), "unit": "samples/s", "cores": r["cores"],
+               "host_cores": r["host_cores"], "kind": r["kind"], "sample": r["sample"]}
 
     if rank == 0:
         line = {

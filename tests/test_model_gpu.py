@@ -10,6 +10,8 @@ gradients: normwise relative error <= 2e-2 (fp16) / 4e-2 (bf16); integer indexin
 Rows where attention_mask == 0 must be exactly zero (documented divergence from the reference,
 which returns garbage there).
 """
+import hashlib
+
 import numpy as np
 import pytest
 import torch
@@ -132,18 +134,32 @@ def test_gradient_fingerprints_c1b(dtype):
     ((((out.float() * m[..., None]) ** 2).sum() / m.sum() / out.size(-1)) * scale).backward()
     bad = []
     typical = float(np.median([g[k][0] for k in g if k.startswith("gfp/")]))
+    checked = 0
     for name, p in model.named_parameters():
         key = "gfp/" + name
         if key not in g or p.grad is None:
             continue
-        fp = g[key]
-        nrm = p.grad.float().norm().item() / scale
+        fp = g[key]                      # [l2 norm, sum, 16 sampled entries] of the reference gradient
+        ours = p.grad.float().cpu().reshape(-1).double() / scale
+        nrm = ours.norm().item()
         if fp[0] < 1e-6 * typical:      # mathematically zero (key.bias): ours must be small noise
             if nrm > 0.1 * typical:
-                bad.append((name, nrm, fp[0]))
+                bad.append((name, "norm", nrm, fp[0]))
             continue
         if abs(nrm - fp[0]) > 3e-2 * max(fp[0], 0.05 * typical):
-            bad.append((name, nrm, fp[0]))
+            bad.append((name, "norm", nrm, fp[0]))
+        # the sum and the 16 sampled entries pin sign, position and layout (a permuted or
+        # sign-flipped gradient keeps its norm); same sampling as make_goldens.grad_fingerprint
+        h = int(hashlib.sha1(name.encode()).hexdigest()[:8], 16)
+        idx = torch.randint(0, ours.numel(), (16,), generator=torch.Generator().manual_seed(h & 0x7FFFFFFF))
+        samp, want = ours[idx], torch.from_numpy(fp[2:])
+        floor = 0.05 * fp[0] / ours.numel() ** 0.5
+        if (samp - want).abs().sum().item() > 5e-2 * (want.abs().sum().item() + 16 * floor):
+            bad.append((name, "samples", samp.tolist()[:4], want.tolist()[:4]))
+        if abs(ours.sum().item() - fp[1]) > 3e-2 * ours.abs().sum().item() + 1e-12:
+            bad.append((name, "sum", ours.sum().item(), fp[1]))
+        checked += 1
+    assert checked >= 20
     assert not bad, bad[:5]
 
 
@@ -473,3 +489,71 @@ def test_pack_meta_cache_is_bound_to_the_tensor_object_not_its_address():
     register_lengths(m3, [56, 50], prefix=True)
     assert UniterModel._pack_meta(m3)["total"] == 106
     assert torch.equal(UniterModel._pack_meta(m3)["pack_idx"], UniterModel._pack_meta(m2)["pack_idx"])
+
+
+def test_non_prefix_attention_mask_end_to_end():
+    """attention_mask with HOLES (no reference collate emits one, but model/model.py:342-345 accepts
+    any 0/1 pattern): the valid tokens are packed in order (the `nonzero_static` branch of
+    _pack_meta), masked keys are omitted, outputs / gradients at valid rows match the oracle and
+    masked rows are exactly zero."""
+    cfg, dtype = util.TINY, torch.float16
+    state = util.make_state(cfg)
+    model = util.make_model(cfg, state, dtype).eval()
+    batch = dict(util.tiny_batch())
+    am = batch["attn_masks"].clone()
+    gen = torch.Generator().manual_seed(5)
+    holes = torch.rand(am.shape, generator=gen) < 0.3
+    holes[:, 0] = False
+    am = am * (~holes).long()
+    assert not all((row[:int(row.sum())] == 1).all() for row in am), "mask must not be a prefix mask"
+    batch["attn_masks"] = am
+    out = _fwd(model, batch, output_all_encoded_layers=False)
+    rs = {k: v.half().float().requires_grad_(True) for k, v in state.items()}
+    ref = orc.uniter_forward(rs, 2, 2, batch["input_ids"], batch["position_ids"],
+                             batch["img_feat"].half().float(), batch["img_pos_feat"].half().float(),
+                             am, batch["gather_index"], output_all_encoded_layers=False)
+    v = am.bool()
+    _assert_close(out.float().cpu()[v], ref.detach()[v], dtype, "non-prefix mask")
+    assert (out.float().cpu()[~v] == 0).all()
+    m = am.float().cuda()
+    (((out.float() * m[..., None]) ** 2).sum() / m.sum() * 64).backward()
+    mc = am.float()
+    (((ref * mc[..., None]) ** 2).sum() / mc.sum() * 64).backward()
+    for name in ("encoder.layer.0.attention.self.query.weight", "encoder.layer.1.output.dense.weight",
+                 "embeddings.word_embeddings.weight", "img_embeddings.img_linear.weight"):
+        got = dict(model.named_parameters())[name].grad.float().cpu()
+        want = rs[name].grad
+        rel = ((got - want).norm() / (want.norm() + 1e-12)).item()
+        assert rel < 4e-2, (name, rel)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_c5_shaped_sequences_up_to_128_and_beyond_end_to_end(dtype):
+    """BASELINE configs[4] shapes (train_itm_hard_negatives.py): text up to 62 tokens + 36..66
+    regions, S in 98..128 — the attention kernels' single-block path with S > 64 (no head pairing)
+    inside the MODEL — plus two sequences > 128 that take the multi-block (nq / nkv > 1) branches."""
+    from uniter_b200.synth import synth_batch
+    cfg = _cfg(128, 2, 512, 2, img_dim=64)
+    state = util.make_state(cfg, seed=7)
+    model = util.make_model(cfg, state, dtype).eval()
+    tl = [62, 40, 8, 62, 30, 100, 120]
+    nb = [36, 66, 36, 66, 36, 66, 100]          # S = 98, 106, 44, 128, 66, 166, 220
+    batch = synth_batch(len(tl), 0, 0, 0, 0, seed=13, img_dim=64, vocab_size=2000, txt_lens=tl, num_bbs=nb)
+    out = _fwd(model, batch, output_all_encoded_layers=False)
+    rs = {k: v.to(dtype).float().requires_grad_(True) for k, v in state.items()}
+    ref = orc.uniter_forward(rs, 2, 2, batch["input_ids"], batch["position_ids"],
+                             batch["img_feat"].to(dtype).float(), batch["img_pos_feat"].to(dtype).float(),
+                             batch["attn_masks"], batch["gather_index"], output_all_encoded_layers=False)
+    v = _valid(batch)
+    _assert_close(out.float().cpu()[v], ref.detach()[v], dtype, "C5 shapes")
+    m = batch["attn_masks"].float().cuda()
+    (((out.float() * m[..., None]) ** 2).sum() / m.sum() * 64).backward()
+    mc = batch["attn_masks"].float()
+    (((ref * mc[..., None]) ** 2).sum() / mc.sum() * 64).backward()
+    for name in ("encoder.layer.0.attention.self.query.weight", "encoder.layer.0.attention.self.key.weight",
+                 "encoder.layer.1.attention.self.value.weight", "encoder.layer.1.output.dense.weight",
+                 "encoder.layer.0.attention.self.value.bias"):
+        got = dict(model.named_parameters())[name].grad.float().cpu()
+        want = rs[name].grad
+        rel = ((got - want).norm() / (want.norm() + 1e-12)).item()
+        assert rel < GRAD_TOL[dtype], (name, rel)
