@@ -46,6 +46,10 @@ def parse():
                     help="N>1: layer groups whose gradient all-reduce overlaps the backward pass")
     ap.add_argument("--sm-reserve", type=int, default=0,
                     help="N>1: SMs left to the overlapped all-reduce (and its CTA cap)")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="enqueue every step from Python (eager) instead of replaying CUDA graphs")
+    ap.add_argument("--token-bucket", type=int, default=128,
+                    help="graph mode: token counts are padded to a multiple of this with a dummy sequence")
     ap.add_argument("--layers", type=int, default=BASE["NL"], help=argparse.SUPPRESS)
     return ap.parse_args()
 
@@ -244,9 +248,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from uniter_b200 import _lib
+    from uniter_b200.arena import GradArena
+    from uniter_b200.graphed import GraphedStep
     from uniter_b200.model import UniterConfig, register_lengths
     from uniter_b200.heads import UniterForMLM
-    from uniter_b200.synth import synth_batch
+    from uniter_b200.synth import pad_mlm_index, synth_batch
     from uniter_b200 import distributed as ubd
 
     lib = _lib.load()
@@ -262,36 +268,47 @@ def main():
     model = UniterForMLM(cfg, BASE["img_dim"]).to(device=dev, dtype=dtype).train()
     if world > 1:
         ubd.broadcast_parameters(model, root=0)
+    GradArena.attach(model)          # one flat gradient buffer: head | pooler | layers | front-end
     reducer = (ubd.GradientReducer(model, overlap_chunks=args.overlap_chunks, sm_reserve=args.sm_reserve)
                if world > 1 else None)
 
-    # ---- synthetic batches (per-rank seed), host side pinned
+    # ---- synthetic batches (per-rank seed), host side pinned; masked-token lists padded to a
+    # multiple of 64 so that every batch of a token bucket replays the same graph
     n_host = 4
     host = []
     for i in range(n_host):
         b = synth_batch(C2["B"], C2["tl"][0], C2["tl"][1], C2["nbb"][0], C2["nbb"][1],
                         C2["seed"] + 1000 * rank + (i if i else 0), mlm_prob=C2["mlm_prob"])
+        b = pad_mlm_index(b, 64)
         hb = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()}
+        hb["lens"] = [a + c for a, c in zip(b["txt_lens"], b["num_bbs"])]
         host.append(hb)
-    lens0 = [a + b for a, b in zip(host[0]["txt_lens"], host[0]["num_bbs"])]
+    lens0 = host[0]["lens"]
     tensor_keys = [k for k, v in host[0].items() if torch.is_tensor(v)]
     h2d_bytes = sum(host[0][k].numel() * host[0][k].element_size() for k in tensor_keys)
 
-    def to_device(hb, stream=None):
-        with torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream()):
+    def loss_fn(batch):
+        # the reference's `loss.mean()` over the masked tokens (pretrain.py:297) with a fixed-size
+        # (padded) token list: padding rows contribute 0, the divisor is the true count
+        return (model(batch).sum() * batch["mlm_inv_n"]).squeeze()
+
+    graphed = None if args.no_graph else GraphedStep(model, loss_fn, token_bucket=args.token_bucket,
+                                                     reducer=reducer)
+
+    def to_device(hb, stream):
+        with torch.cuda.stream(stream):
             d = {k: hb[k].to(dev, non_blocking=True) for k in tensor_keys}
-        register_lengths(d["attn_masks"], [a + b for a, b in zip(hb["txt_lens"], hb["num_bbs"])],
-                         prefix=True)
         return d
 
-    def step(batch):
+    def eager_step(batch, lens):
+        register_lengths(batch["attn_masks"], lens, prefix=True)
         model.zero_grad(set_to_none=True)
-        loss = model(batch).mean()
+        loss = loss_fn(batch)
         if reducer is not None:
             reducer.backward_and_reduce(loss)
         else:
             loss.backward()
-        return loss
+        return loss.detach()
 
     def barrier():
         if world > 1:
@@ -313,11 +330,18 @@ def main():
             ms = t.item()
         return ms
 
-    # ---- resident-input measurement ("value")
-    resident = to_device(host[0])
+    # ---- resident-input measurement ("value"): inputs already in HBM, the step is replayed
+    resident = to_device(host[0], torch.cuda.current_stream())
     torch.cuda.synchronize()
-    for i in range(args.warmup):
-        step(resident)
+    if graphed is not None:
+        bk0 = graphed.stage(resident, lens0)          # captures the bucket of batch 0 (untimed)
+        for i in range(args.warmup):
+            bk0.graph.replay()
+        step_resident = lambda i: bk0.graph.replay()  # noqa: E731
+    else:
+        for i in range(args.warmup):
+            eager_step(resident, lens0)
+        step_resident = lambda i: eager_step(resident, lens0)  # noqa: E731
     torch.cuda.synchronize()
     launches0 = lib.ub200_launch_count()
     sampler = ClockSampler(local_rank)
@@ -327,16 +351,21 @@ def main():
 
     def timed_step(i):
         t0 = time.perf_counter()
-        step(resident)
+        step_resident(i)
         cpu_t[0] += time.perf_counter() - t0
 
     ms_total = timed(timed_step, args.steps)
     cpu_enqueue_ms = cpu_t[0] / args.steps * 1e3   # host time to enqueue one step (no sync inside)
-    launches = (lib.ub200_launch_count() - launches0) // args.steps
+    if graphed is not None:
+        launches = bk0.launches                    # libub200 kernels inside one replay of the graph
+    else:
+        launches = (lib.ub200_launch_count() - launches0) // args.steps
     ms_step = ms_total / args.steps
     value = C2["B"] * world / (ms_step * 1e-3)
 
-    # ---- e2e: host batches from pinned memory, prefetched on a side stream, loss read back
+    # ---- e2e: host batches from pinned memory, H2D on a copy stream into rotating device staging
+    # buffers while the previous step computes, device-to-device into the graph's static inputs,
+    # replay, loss read back asynchronously
     copy_stream = torch.cuda.Stream()
     state = {}
 
@@ -348,14 +377,22 @@ def main():
     loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
     loss_events = [torch.cuda.Event(), torch.cuda.Event()]
     losses = []
+    e2e_cpu = [0.0]
 
     def e2e_step(i):
+        t0 = time.perf_counter()
         torch.cuda.current_stream().wait_stream(copy_stream)
-        batch, _ = state["next"]
+        batch, hb = state["next"]
         for t in batch.values():
             t.record_stream(torch.cuda.current_stream())
-        prefetch(i + 1)
-        loss = step(batch)
+        if graphed is not None:
+            bk = graphed.stage(batch, hb["lens"])
+            prefetch(i + 1)
+            bk.graph.replay()
+            loss = bk.loss
+        else:
+            prefetch(i + 1)
+            loss = eager_step(batch, hb["lens"])
         # D2H read of the step's result: asynchronous copy into pinned memory, consumed while the
         # next step is already enqueued (a blocking .item() here would drain the GPU queue every
         # step, which the reference's own loop does, train_vqa.py:201 — noted, not copied)
@@ -365,18 +402,24 @@ def main():
         if i > 0:
             loss_events[slot ^ 1].synchronize()
             losses.append(float(loss_host[slot ^ 1]))
+        e2e_cpu[0] += time.perf_counter() - t0
 
-    # warm-up covers every distinct host batch once (each has its own token count, so the caching
-    # allocator sees its block sizes before the timed region), and the batch rotation continues
-    # across the warm-up / timed boundary
+    # warm-up covers every distinct host batch once (each has its own token count: graph buckets are
+    # captured / the caching allocator sees its block sizes before the timed region), and the batch
+    # rotation continues across the warm-up / timed boundary
     prefetch(0)
     n_warm = max(args.warmup, n_host + 1)
     for i in range(n_warm):
         e2e_step(i)
+    e2e_cpu[0] = 0.0
     ms_e2e = timed(lambda i: e2e_step(n_warm + i), args.steps) / args.steps
+    e2e_host_ms = e2e_cpu[0] / args.steps * 1e3
     clocks = sampler.stop() if rank == 0 else None     # sampled across both timed regions (under load)
     assert all(l == l for l in losses), "NaN loss in the e2e leg"
     e2e_value = C2["B"] * world / (ms_e2e * 1e-3)
+
+    def step(batch):                                   # eager step for the per-launch event pass
+        return eager_step(batch, lens0)
 
     # ---- per-kernel-role pass (CUDA events around every launch on the launching stream)
     breakdown, roofline = None, None
@@ -471,7 +514,14 @@ def main():
                        "l2": "per-step working set (weights 0.22 GB + saved activations ~1 GB) exceeds the "
                              "126 MB L2; no explicit flush"},
             "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "ms_per_step": round(ms_e2e, 4),
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "host_ms_per_step": round(e2e_host_ms, 3),
+                    "batches": "%d distinct pinned host batches in rotation (T = %s)"
+                               % (n_host, ", ".join(str(sum(h["lens"])) for h in host))},
+            "step_mode": ("eager (Python enqueues every launch)" if graphed is None else
+                          "cuda_graph: fwd+bwd%s replayed per token bucket of %d (%d graphs captured, "
+                          "dummy-sequence padding)" % (" + gradient all-reduce" if reducer is not None else "",
+                                                       args.token_bucket, graphed.captures)),
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(cpu_enqueue_ms, 3),
             "algorithmic_tflops_per_step": round(flops_step / 1e12, 4),
             "achieved_tflops": round(flops_step / (ms_step * 1e-3) / 1e12, 1),

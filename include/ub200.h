@@ -124,6 +124,9 @@ typedef struct {
                               b_major == 0, columns if b_major == 1): the rest contribute acc = 0.
                               Lets N be padded to a multiple of 8 over an unpadded weight (the tied
                               decoder [28996, H] of model/layer.py:206-222) */
+  const uint64_t* rng_offset_dev; /* optional DEVICE counter: the dropout stream used is
+                              rng_stream + (*rng_offset_dev << 20).  Lets a CUDA graph replay the same
+                              launch with fresh masks (the host bumps the counter, not the arguments) */
 } ub200_gemm_args;
 
 int ub200_gemm(const ub200_gemm_args* args, ub200_stream_t stream);
@@ -158,6 +161,7 @@ typedef struct {
   void* workspace;            /* bwd: fp32 dQ accumulator or NULL */
   float* dbias;               /* bwd, optional: [3H] fp32, += column sums of dqkv = gradient of the
                                  stacked query|key|value biases (fused; saves a pass over dqkv) */
+  const uint64_t* rng_offset_dev; /* optional device counter added to rng_stream (see ub200_gemm_args) */
 } ub200_attn_args;
 
 int ub200_attn_fwd(const ub200_attn_args* args, ub200_stream_t stream);
@@ -195,6 +199,7 @@ typedef struct {
   int32_t kind;
   int32_t dropout_on_dy;    /* bit 0: y = dropout(LN(x)) (embeddings): mask dy instead of emitting dx_drop;
                                bit 1: with row_kind, rows of the OTHER kind get dx = 0 (else untouched) */
+  const uint64_t* rng_offset_dev; /* optional device counter added to rng_stream (see ub200_gemm_args) */
 } ub200_ln_bwd_args;
 int ub200_layernorm_bwd(const ub200_ln_bwd_args* args, ub200_stream_t stream);
 
@@ -254,6 +259,8 @@ typedef struct {
   uint64_t rng_seed, rng_offset; /* rng_offset must differ between forward calls */
   int32_t layer_offset;          /* index of layers[0] in the whole stack (dropout streams are keyed
                                     by the global layer index, so a backward may be issued in chunks) */
+  const uint64_t* rng_offset_dev; /* optional DEVICE counter added to rng_offset at run time: a captured
+                                    CUDA graph of the step draws new dropout masks on every replay */
 } ub200_encoder_desc;
 
 /* bytes of saved activations per layer (fwd writes, bwd reads) and of backward scratch */
@@ -318,6 +325,7 @@ typedef struct {
   int32_t T, hidden, dtype;
   float dropout_p;
   uint64_t rng_seed, rng_stream;
+  const uint64_t* rng_offset_dev; /* optional device counter added to rng_stream (see ub200_gemm_args) */
 } ub200_embed_rows_args;
 int ub200_embed_rows_fwd(const ub200_embed_rows_args* args, ub200_stream_t stream);
 

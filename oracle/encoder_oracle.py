@@ -135,7 +135,8 @@ def uniter_forward(state, num_layers, num_heads, input_ids, position_ids, img_fe
                    taps=None):
     """model/model.py:336-367 (UniterModel.forward), padded [B, L] rectangle exactly as the
     reference computes it, including its garbage at masked query rows."""
-    ext_mask = (1.0 - attention_mask[:, None, None, :].to(torch.float32)) * -10000.0  # :342-345
+    pdtype = next(iter(state.values())).dtype           # :343-344 "fp16 compatibility": param dtype
+    ext_mask = (1.0 - attention_mask[:, None, None, :].to(pdtype)) * -10000.0         # :342-345
     if input_ids is None:                                                              # :348-351
         x = image_embeddings(state, img_feat, img_pos_feat, img_type_ids, img_masks)
     elif img_feat is None:                                                             # :352-355

@@ -218,21 +218,28 @@ def test_reference_heads_accept_the_drop_in_model():
 
 
 def test_prefix_pack_bookkeeping_matches_mask_derived_indices():
-    """Host-side packing metadata (no device reads) == what the mask itself implies."""
+    """Host-side packing metadata (no device reads) == what the mask itself implies; with a token
+    bucket (`T_pad`) the padding is one dummy sequence that no output position references."""
     from uniter_b200.model import _prefix_pack_host
-    for lens, L in (([56, 44], 56), ([1], 1), ([3, 7, 2, 7], 9), ([5] * 64, 72), ([0, 4, 0], 4)):
+    for lens, L, T_pad in (([56, 44], 56, None), ([1], 1, None), ([3, 7, 2, 7], 9, None),
+                           ([5] * 64, 72, 384), ([0, 4, 0], 4, 8), ([3, 7, 2, 7], 9, 19)):
         B, T = len(lens), sum(lens)
         mask = torch.zeros(B, L, dtype=torch.long)
         for b, s in enumerate(lens):
             mask[b, :s] = 1
-        host, (o_cu, o_pack, o_unpack) = _prefix_pack_host(lens, L)
-        assert host.dtype == torch.int32 and o_pack % 4 == 0 and o_unpack % 4 == 0
-        cu = host[o_cu:o_cu + B + 1]
-        pack = host[o_pack:o_pack + T]
-        unpack = host[o_unpack:o_unpack + B * L]
-        assert cu.tolist() == [0] + torch.tensor(lens).cumsum(0).tolist()
+        host, o, T_out = _prefix_pack_host(lens, L, T_pad)
+        Tp = T if T_pad is None else T_pad
+        assert T_out == T
+        assert host.dtype == torch.int32 and o["pack"] % 4 == 0 and o["inv"] % 4 == 0 and o["unpack"] % 4 == 0
+        cu = host[o["cu"]:o["cu"] + B + 2]
+        pack = host[o["pack"]:o["pack"] + Tp]
+        inv = host[o["inv"]:o["inv"] + Tp]
+        unpack = host[o["unpack"]:o["unpack"] + B * L + 1]
+        assert cu.tolist() == [0] + torch.tensor(lens).cumsum(0).tolist() + [Tp]
         want_pack = mask.reshape(-1).nonzero().squeeze(1).to(torch.int32)
-        assert torch.equal(pack, want_pack)
-        want_unpack = torch.full((B * L,), -1, dtype=torch.int32)
+        assert torch.equal(pack[:T], want_pack) and torch.equal(inv[:T], want_pack)
+        # dummy rows: computed from a valid position, invisible to the inverse map
+        assert (inv[T:] == -1).all() and (pack[T:] == (want_pack[0] if T else 0)).all()
+        want_unpack = torch.full((B * L + 1,), -1, dtype=torch.int32)
         want_unpack[want_pack.long()] = torch.arange(T, dtype=torch.int32)
-        assert torch.equal(unpack, want_unpack)
+        assert torch.equal(unpack, want_unpack) and unpack[-1] == -1

@@ -37,17 +37,17 @@ def _worker(rank, world, port, out):
         ubd.broadcast_parameters(model, root=0)
         sd = {k: v.clone() for k, v in model.state_dict().items()}
         # fake per-rank gradients: encoder-layer grads live in the arena (as after a real backward),
-        # everything else gets ordinary .grad tensors
-        enc = model.uniter
-        A = enc._build_arena()
+        # everything else gets ordinary .grad tensors (as autograd would assign them)
+        from uniter_b200.arena import GradArena
+        arena = GradArena.attach(model)
         g = torch.Generator().manual_seed(7 + rank)
-        A["flat"].copy_(torch.randn(A["flat"].shape, generator=g))
-        arena_params = set()
-        for p, v in A["views"]:
-            p.grad = v
-            arena_params.add(id(p))
+        arena.flat.copy_(torch.randn(arena.flat.shape, generator=g))
+        enc = model.uniter
+        layer_ids = set(id(p) for p in enc.encoder.parameters())
         for p in model.parameters():
-            if id(p) not in arena_params:
+            if id(p) in layer_ids:
+                p.grad = arena.view(p)
+            else:
                 p.grad = torch.randn(p.shape, generator=g)
         local = {n: p.grad.clone() for n, p in model.named_parameters()}
         ubd.GradientReducer(model).reduce()
@@ -73,5 +73,5 @@ def test_broadcast_and_gradient_mean_two_ranks():
         want = orc.allreduce_mean([loc0[n], loc1[n]])[0]
         assert torch.allclose(red0[n], want, atol=1e-6), n
         assert torch.equal(red0[n], red1[n]), n
-    # the encoder-layer gradients were reduced in place inside ONE flat arena (no copy-in/out)
+    # every gradient ended up inside ONE flat arena and was reduced there in place (no copy-in/out)
     assert "uniter.encoder.layer.0.attention.self.query.weight" in loc0

@@ -47,6 +47,6 @@ def test_gradient_reducer_chunked_backward_single_rank_nccl():
                 assert torch.allclose(p.grad.float(), ref[n].float(), atol=2e-3, rtol=2e-2), n
         # the encoder-layer gradients were reduced in place inside the arena
         q = model.uniter.encoder.layer[0].attention.self.query.weight
-        assert q.grad.data_ptr() == model.uniter._arena["views"][0][1].data_ptr()
+        assert q.grad.data_ptr() == model.uniter._ensure_arena()[0].view(q).data_ptr()
     finally:
         dist.destroy_process_group()

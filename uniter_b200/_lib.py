@@ -29,6 +29,7 @@ class GemmArgs(C.Structure):
         ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64),
         ("tile_n", C.c_int32), ("max_ctas", C.c_int32), ("cluster", C.c_int32),
         ("k_splits", C.c_int32), ("n_valid", C.c_int32),
+        ("rng_offset_dev", C.c_void_p),
     ]
 
 
@@ -39,6 +40,7 @@ class AttnArgs(C.Structure):
         ("hidden", C.c_int32), ("num_heads", C.c_int32), ("dtype", C.c_int32),
         ("dropout_p", C.c_float), ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64),
         ("dctx", C.c_void_p), ("dqkv", C.c_void_p), ("workspace", C.c_void_p), ("dbias", C.c_void_p),
+        ("rng_offset_dev", C.c_void_p),
     ]
 
 
@@ -49,6 +51,7 @@ class LnBwdArgs(C.Structure):
         ("rows", C.c_int32), ("hidden", C.c_int32), ("dtype", C.c_int32),
         ("dropout_p", C.c_float), ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64),
         ("row_kind", C.c_void_p), ("kind", C.c_int32), ("dropout_on_dy", C.c_int32),
+        ("rng_offset_dev", C.c_void_p),
     ]
 
 
@@ -70,7 +73,8 @@ class EmbedRowsArgs(C.Structure):
         "ln_txt_g", "ln_txt_b", "img_linear_out", "pos_feat", "w_pos", "b_pos",
         "ln_img_g", "ln_img_b", "ln_pos_g", "ln_pos_b", "ln_out_g", "ln_out_b", "x", "u", "ppre")] + [
         ("T", C.c_int32), ("hidden", C.c_int32), ("dtype", C.c_int32),
-        ("dropout_p", C.c_float), ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64)]
+        ("dropout_p", C.c_float), ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64),
+        ("rng_offset_dev", C.c_void_p)]
 
 
 class EmbedColsumArgs(C.Structure):

@@ -44,6 +44,7 @@ struct AttnParams {
   const void* dctx;        // [T, H]
   void* dqkv;              // [T, 3H]
   float* dbias;            // [3H] fp32 column sums of dqkv (QKV bias gradient), accumulated; or NULL
+  const unsigned long long* rng_dev;   // optional device-side dropout stream offset (graph replay)
 };
 
 // Column sums over the 32 rows (= lanes) of a warp of a 32-column register block: a butterfly in
@@ -99,6 +100,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (pair && static_cast<int>(blockIdx.y) >= p.nheads / 2) return;
   const int h0 = pair ? 2 * blockIdx.y : blockIdx.y;
   const int nkv = (S + ATT_BN - 1) / ATT_BN;   // 1 in pair mode
+  uint32_t rs0 = p.stream_lo, rs1 = p.stream_hi;
+  if (p.drop_thr16) rng_add_dev_offset(p.rng_dev, rs0, rs1);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -239,7 +242,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         }
         if (p.drop_thr16) {
           DropoutRng rng;
-          rng.k0 = p.seed_lo; rng.k1 = p.seed_hi; rng.s0 = p.stream_lo; rng.s1 = p.stream_hi;
+          rng.k0 = p.seed_lo; rng.k1 = p.seed_hi; rng.s0 = rs0; rng.s1 = rs1;
           const uint4 rnd = rng.draw8(attn_drop_group(bh, qrow, j * ATT_BN + key0));
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -341,6 +344,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int h0 = pair ? 2 * blockIdx.y : blockIdx.y;
   const int nq = (S + ATT_BM - 1) / ATT_BM;
   const int nkv = (S + ATT_BN - 1) / ATT_BN;
+  uint32_t rs0 = p.stream_lo, rs1 = p.stream_hi;
+  if (p.drop_thr16) rng_add_dev_offset(p.rng_dev, rs0, rs1);
   const int kv_len = pair ? S : min(ATT_BN, S - j * ATT_BN);
   const int n_pad = pair ? ATT_BN : ((kv_len + 15) & ~15);
 
@@ -466,7 +471,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         uint4 rnd = make_uint4(0, 0, 0, 0);
         if (p.drop_thr16) {
           DropoutRng rng;
-          rng.k0 = p.seed_lo; rng.k1 = p.seed_hi; rng.s0 = p.stream_lo; rng.s1 = p.stream_hi;
+          rng.k0 = p.seed_lo; rng.k1 = p.seed_hi; rng.s0 = rs0; rng.s1 = rs1;
           rnd = rng.draw8(attn_drop_group(bh, qrow, j * ATT_BN + key0));
         }
 #pragma unroll
@@ -669,6 +674,7 @@ extern "C" int ub200_attn_fwd(const ub200_attn_args* args, ub200_stream_t stream
   p.seed_lo = static_cast<uint32_t>(a.rng_seed); p.seed_hi = static_cast<uint32_t>(a.rng_seed >> 32);
   p.stream_lo = static_cast<uint32_t>(a.rng_stream);
   p.stream_hi = static_cast<uint32_t>(a.rng_stream >> 32);
+  p.rng_dev = reinterpret_cast<const unsigned long long*>(a.rng_offset_dev);
 
   dim3 grid((a.max_seqlen + ATT_BM - 1) / ATT_BM, a.num_heads, a.batch);
   static bool configured[2] = {false, false};
@@ -740,6 +746,7 @@ extern "C" int ub200_attn_bwd(const ub200_attn_args* args, ub200_stream_t stream
   p.seed_lo = static_cast<uint32_t>(a.rng_seed); p.seed_hi = static_cast<uint32_t>(a.rng_seed >> 32);
   p.stream_lo = static_cast<uint32_t>(a.rng_stream);
   p.stream_hi = static_cast<uint32_t>(a.rng_stream >> 32);
+  p.rng_dev = reinterpret_cast<const unsigned long long*>(a.rng_offset_dev);
   float* acc = reinterpret_cast<float*>(a.workspace);
   if (multi)
     UB_CHECK_CUDA(cudaMemsetAsync(acc, 0, static_cast<size_t>(a.total_tokens) * a.hidden * 4, stream));

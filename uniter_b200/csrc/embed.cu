@@ -145,6 +145,7 @@ struct RowsParams {
   int T, H;
   uint32_t drop_thr16; float drop_inv_keep;
   uint32_t seed_lo, seed_hi, stream_lo, stream_hi;
+  const unsigned long long* rng_dev;   // optional device-side dropout stream offset (graph replay)
 };
 
 template <bool kBF16, int NV>
@@ -274,6 +275,7 @@ embed_rows_fwd_kernel(const RowsParams p) {
   // ---- dropout + store
   DropoutRng rng;
   rng.k0 = p.seed_lo; rng.k1 = p.seed_hi; rng.s0 = p.stream_lo; rng.s1 = p.stream_hi;
+  if (p.drop_thr16) rng_add_dev_offset(p.rng_dev, rng.s0, rng.s1);
   uint4* xrow = reinterpret_cast<uint4*>(reinterpret_cast<T16*>(p.x) + static_cast<size_t>(t) * H);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -497,6 +499,7 @@ extern "C" int ub200_embed_rows_fwd(const ub200_embed_rows_args* a, ub200_stream
   }
   p.seed_lo = static_cast<uint32_t>(a->rng_seed); p.seed_hi = static_cast<uint32_t>(a->rng_seed >> 32);
   p.stream_lo = static_cast<uint32_t>(a->rng_stream); p.stream_hi = static_cast<uint32_t>(a->rng_stream >> 32);
+  p.rng_dev = reinterpret_cast<const unsigned long long*>(a->rng_offset_dev);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int grid = (a->T + 7) / 8;
   const int nv = (a->hidden + 255) / 256;

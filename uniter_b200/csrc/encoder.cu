@@ -88,6 +88,7 @@ static ub200_gemm_args gemm_base(const ub200_encoder_desc* d) {
   ub200_gemm_args g{};
   g.dtype = d->dtype;
   g.rng_seed = d->rng_seed;
+  g.rng_offset_dev = d->rng_offset_dev;
   return g;
 }
 
@@ -146,6 +147,7 @@ extern "C" int ub200_encoder_fwd(const ub200_encoder_desc* d, const ub200_layer_
     at.max_seqlen = d->max_seqlen; at.hidden = H; at.num_heads = d->num_heads; at.dtype = d->dtype;
     at.dropout_p = d->attn_dropout_p; at.rng_seed = d->rng_seed;
     at.rng_stream = rng_stream_of(d, l, SITE_ATTN_PROBS);
+    at.rng_offset_dev = d->rng_offset_dev;
     {
       ProfTag _t(2);
       UB_TRY(ub200_attn_fwd(&at, stream));
@@ -243,6 +245,7 @@ extern "C" int ub200_encoder_bwd(const ub200_encoder_desc* d, const ub200_layer_
     ln.dgamma = gr.small + SG.dg2; ln.dbeta = gr.small + SG.db2ln; ln.dbias = gr.small + SG.db2;
     ln.rows = T; ln.hidden = H; ln.dtype = d->dtype; ln.dropout_p = d->hidden_dropout_p;
     ln.rng_seed = d->rng_seed; ln.rng_stream = rng_stream_of(d, l, SITE_FFN_OUT);
+    ln.rng_offset_dev = d->rng_offset_dev;
     {
       ProfTag _t(8);
       UB_TRY(ub200_layernorm_bwd(&ln, stream));
@@ -274,6 +277,7 @@ extern "C" int ub200_encoder_bwd(const ub200_encoder_desc* d, const ub200_layer_
     ln.dgamma = gr.small + SG.dg1; ln.dbeta = gr.small + SG.db1ln; ln.dbias = gr.small + SG.dbo;
     ln.rows = T; ln.hidden = H; ln.dtype = d->dtype; ln.dropout_p = d->hidden_dropout_p;
     ln.rng_seed = d->rng_seed; ln.rng_stream = rng_stream_of(d, l, SITE_ATTN_OUT);
+    ln.rng_offset_dev = d->rng_offset_dev;
     {
       ProfTag _t(13);
       UB_TRY(ub200_layernorm_bwd(&ln, stream));
@@ -297,6 +301,7 @@ extern "C" int ub200_encoder_bwd(const ub200_encoder_desc* d, const ub200_layer_
     at.max_seqlen = d->max_seqlen; at.hidden = H; at.num_heads = d->num_heads; at.dtype = d->dtype;
     at.dropout_p = d->attn_dropout_p; at.rng_seed = d->rng_seed;
     at.rng_stream = rng_stream_of(d, l, SITE_ATTN_PROBS);
+    at.rng_offset_dev = d->rng_offset_dev;
     at.dctx = sc + S.bufC; at.dqkv = sc + S.dqkv; at.workspace = attn_ws ? sc + S.attn_ws : nullptr;
     at.dbias = gr.small + SG.dbqkv;   // dbqkv = colsum(dqkv), fused into the attention backward
     {

@@ -119,6 +119,7 @@ extern "C" int ub200_gemm(const ub200_gemm_args* args, ub200_stream_t stream_) {
   p.seed_hi = static_cast<uint32_t>(a.rng_seed >> 32);
   p.stream_lo = static_cast<uint32_t>(a.rng_stream);
   p.stream_hi = static_cast<uint32_t>(a.rng_stream >> 32);
+  p.rng_dev = reinterpret_cast<const unsigned long long*>(a.rng_offset_dev);
   p.tiles_m = (a.M + BM - 1) / BM;
   p.tiles_n = (a.N + bn - 1) / bn;
   const int num_kb = (a.K + BK - 1) / BK;

@@ -283,6 +283,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmParams& p, uint32_t t_ac
 __device__ __forceinline__ DropoutRng make_rng(const GemmParams& p) {
   DropoutRng rng;
   rng.k0 = p.seed_lo; rng.k1 = p.seed_hi; rng.s0 = p.stream_lo; rng.s1 = p.stream_hi;
+  if (p.epilogue & UB200_EPI_DROPOUT) rng_add_dev_offset(p.rng_dev, rng.s0, rng.s1);
   rng.thr16 = p.drop_thr16; rng.inv_keep = p.drop_inv_keep;
   return rng;
 }

@@ -20,6 +20,7 @@ struct GemmParams {
   uint32_t drop_thr16;
   float drop_inv_keep;
   uint32_t seed_lo, seed_hi, stream_lo, stream_hi;
+  const unsigned long long* rng_dev;   // optional device-side stream offset (graph replay)
   int tiles_m, tiles_n;
   int ksplit;          // >= 1: work unit = (tile, k-slice); > 1 needs the fp32 atomic epilogue
   int kb_per_split;    // k-blocks per slice

@@ -320,6 +320,17 @@ struct DropoutRng {
                       k1);
   }
 };
+// Optional device-side stream offset: stream64 += (*dev << 20).  The host-side arguments of a
+// launch are frozen inside a CUDA graph; the counter lives in device memory and is bumped between
+// replays, so every replay draws fresh dropout masks (forward and backward of one replay read the
+// same value).
+__device__ __forceinline__ void rng_add_dev_offset(const unsigned long long* dev, uint32_t& s0, uint32_t& s1) {
+  if (dev != nullptr) {
+    const unsigned long long st = ((static_cast<unsigned long long>(s1) << 32) | s0) + (__ldg(dev) << 20);
+    s0 = static_cast<uint32_t>(st);
+    s1 = static_cast<uint32_t>(st >> 32);
+  }
+}
 __device__ __forceinline__ uint32_t rand16_of(const uint4& r, int lane8) {
   uint32_t w = (lane8 & 4) ? ((lane8 & 2) ? r.w : r.z) : ((lane8 & 2) ? r.y : r.x);
   return (lane8 & 1) ? (w >> 16) : (w & 0xFFFFu);

@@ -109,6 +109,7 @@ struct LnBwdParams {
   int kind;
   int dy_drop;          // 1: the dropout mask applies to dy (y = dropout(LN(x)), embeddings)
   int zero_inactive;    // 1: rows of the other kind get dx = 0 (instead of being left untouched)
+  const unsigned long long* rng_dev;   // optional device-side dropout stream offset (graph replay)
 };
 
 // NV = vectors (8 columns) per lane = ceil(H / 256): register arrays are sized for the actual
@@ -135,6 +136,7 @@ ln_bwd_kernel(const LnBwdParams p) {
   }
   DropoutRng rng;
   rng.k0 = p.seed_lo; rng.k1 = p.seed_hi; rng.s0 = p.stream_lo; rng.s1 = p.stream_hi;
+  if (p.drop_thr16) rng_add_dev_offset(p.rng_dev, rng.s0, rng.s1);
   rng.thr16 = p.drop_thr16; rng.inv_keep = p.drop_inv_keep;
   const float inv_h = 1.0f / H;
 
@@ -528,6 +530,7 @@ extern "C" int ub200_layernorm_bwd(const ub200_ln_bwd_args* a, ub200_stream_t st
   p.seed_lo = static_cast<uint32_t>(a->rng_seed); p.seed_hi = static_cast<uint32_t>(a->rng_seed >> 32);
   p.stream_lo = static_cast<uint32_t>(a->rng_stream);
   p.stream_hi = static_cast<uint32_t>(a->rng_stream >> 32);
+  p.rng_dev = reinterpret_cast<const unsigned long long*>(a->rng_offset_dev);
   return ub::launch_ln_bwd(a->dtype, p, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -3,25 +3,27 @@
 Replaces the Horovod path of the reference (utils/distributed.py):
   * `all_reduce_and_rescale_tensors(grads, 1.0)` (:16-43; call sites train_vqa.py:193-199,
     pretrain.py:302-308) — copy every grad into one flat buffer, `hvd.allreduce_` (Horovod 0.16.4
-    default = AVERAGE over ranks), copy back — becomes `GradientReducer`: the encoder-layer
-    gradients already live in ONE flat arena (`UniterModel.grad_arena()`, parameters' .grad are
-    views of it), so they are all-reduced in place with no copy-in / copy-out; the few remaining
-    parameters (embeddings, pooler, task head) go through one small flat bucket.
+    default = AVERAGE over ranks), copy back — becomes `GradientReducer`: every parameter's .grad
+    already IS a view of one flat arena (uniter_b200.arena.GradArena: task head | pooler | encoder
+    layers | embedding front-end, i.e. the order in which the backward pass finishes them), so the
+    exchange is a handful of in-place all-reduces of arena slices with no copy-in / copy-out,
+    issued on a side stream while the backward of the earlier layers is still running.
   * `broadcast_tensors(params, 0)` (:100-148; train_vqa.py:147) becomes `broadcast_parameters`.
 One process per GPU; the path shards by samples only (pure data parallelism).
 """
 import torch
 import torch.distributed as dist
 
-from .model import UniterModel
+from .arena import GradArena
 
 
 def _avg_all_reduce(t, async_op=False, group=None):
-    """Mean over ranks.  NCCL reduces with AVG directly; gloo (CPU tests) sums then divides."""
-    if dist.get_backend() == "nccl":
+    """Mean over the ranks of `group`.  NCCL reduces with AVG directly; gloo (CPU tests) sums then
+    divides."""
+    if dist.get_backend(group) == "nccl":
         return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op, group=group)
-    w = dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=False)
-    t.div_(dist.get_world_size())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=False, group=group)
+    t.div_(dist.get_world_size(group))
     return None
 
 
@@ -41,42 +43,49 @@ def _capped_nccl_group(max_ctas):
 def broadcast_parameters(model, root=0):
     """Rank `root`'s parameters and buffers -> every rank (startup only)."""
     works = []
+    seen = set()
     for t in list(model.parameters()) + list(model.buffers()):
+        if id(t) in seen:
+            continue
+        seen.add(id(t))
         works.append(dist.broadcast(t.data, src=root, async_op=True))
     for w in works:
         w.wait()
 
 
 class GradientReducer:
-    """Average gradients over ranks after backward: arena in place + one bucket for the rest."""
+    """Average gradients over ranks: in-place all-reduce of slices of the model's gradient arena."""
 
     def __init__(self, model, overlap_chunks=4, sm_reserve=0):
-        """`overlap_chunks` > 1: the encoder arena is all-reduced in that many layer groups while
-        the backward of the earlier layers still runs.  `sm_reserve` > 0: during that overlap the
-        library's persistent kernels leave `sm_reserve` SMs to the collective, and the collective
-        runs on a communicator capped to the same number of CTAs (must be called by all ranks).
-        Measured on 2 x B200 (C2, profiles/r01_scale2_variants.json): no overlap 5.40 ms/step,
-        4 chunks 5.13, 4 chunks + reserve 8 / 16: 5.22 / 5.24 — NCCL's CTAs co-reside with the
-        persistent CTAs well enough that giving up SMs costs more than it saves, hence default 0."""
+        """`overlap_chunks` > 1: the encoder layers are all-reduced in that many groups (top group
+        first, together with the task-head / pooler slice, which is final by then) while the backward
+        of the earlier layers still runs; only the embedding front-end slice is reduced after the
+        backward.  `sm_reserve` > 0: during that overlap the library's persistent kernels leave
+        `sm_reserve` SMs to the collective, and the collective runs on a communicator capped to the
+        same number of CTAs (must be called by all ranks).  Measured on 2 x B200 (C2,
+        profiles/r01_scale2_variants.json): reserving SMs cost more than it saved, hence default 0."""
         self.model = model
+        self.arena = GradArena.attach(model)
+        self.encoders = self.arena.encoders
         self.sm_reserve = int(sm_reserve)
         self._group = None
         self._lib = None
-        if self.sm_reserve > 0 and overlap_chunks > 1 and dist.is_initialized() and dist.get_backend() == "nccl":
+        nccl = dist.is_initialized() and dist.get_backend() == "nccl"
+        if self.sm_reserve > 0 and overlap_chunks > 1 and nccl:
             self._group = _capped_nccl_group(self.sm_reserve)
             from . import _lib
             self._lib = _lib.load()
-        self.encoders = [m for m in model.modules() if isinstance(m, UniterModel)]
-        self._others = None
-        self._flat = None
         self.overlap_chunks = overlap_chunks
         self._pending = []
-        self._reduced = set()
+        self._done = []               # element ranges of the arena already shipped in this step
         self._comm_stream = None
         self._reserved = False
+        self._bwd_seen = {}
 
     # ---- overlap: called by _EncoderStack.backward after the kernels of layers [lo, hi) are enqueued
-    def _on_chunk(self, enc, lo, hi):
+    def _ship(self, lo, hi):
+        if hi <= lo:
+            return
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream()
         ev = torch.cuda.Event()
@@ -86,47 +95,62 @@ class GradientReducer:
             self._reserved = True
         with torch.cuda.stream(self._comm_stream):
             self._comm_stream.wait_event(ev)
-            self._pending.append(_avg_all_reduce(enc.arena_slice(lo, hi), async_op=True, group=self._group))
-        self._reduced.add(id(enc))
+            self._pending.append(_avg_all_reduce(self.arena.flat[lo:hi], async_op=True, group=self._group))
+        self._done.append((lo, hi))
 
-    def _arena_param_ids(self):
-        ids = set()
-        for enc in self.encoders:
-            if enc._arena is None:
-                enc._build_arena()
-            ids.update(id(p) for p, _ in enc._arena["views"])
-        return ids
+    def _on_chunk(self, enc, lo, hi):
+        # an encoder that ran several forwards in this step (model/nlvr2.py runs the same encoder on
+        # two images) accumulates all of them into the same slices: only the LAST backward may ship
+        n = self._bwd_seen.get(id(enc), 0)
+        NL = enc.config.num_hidden_layers
+        if hi == NL:
+            n += 1
+            self._bwd_seen[id(enc)] = n
+        if n < getattr(enc, "_fwd_since_reduce", 1):
+            return
+        ei = self.encoders.index(enc)
+        _, ep = enc._ensure_arena()
+        if hi == NL:
+            # everything downstream of the encoder output (task head, pooler) has finished its backward
+            h_lo, h_hi = self.arena.segments["head"]
+            p_lo, p_hi = self.arena.segments["enc%d.pooler" % ei]
+            if ei == 0 and len(self.encoders) == 1 and h_hi == p_lo:
+                self.arena.fold_foreign_range(h_lo, p_hi)
+                self._ship(h_lo, p_hi)
+        self._ship(ep["layer0"] + lo * ep["per_layer"], ep["layer0"] + hi * ep["per_layer"])
 
     def reduce(self):
-        works = []
-        arena_ids = self._arena_param_ids()
+        """Ship whatever part of the arena has not been shipped yet, then wait for everything."""
+        self.arena.fold_foreign()
+        rest, pos = [], 0
+        for lo, hi in sorted(self._done):
+            if lo > pos:
+                rest.append((pos, lo))
+            pos = max(pos, hi)
+        if pos < self.arena.numel:
+            rest.append((pos, self.arena.numel))
+        works = self._pending
+        self._pending = []
+        cuda = self.arena.flat.is_cuda
+        for lo, hi in rest:
+            if cuda and self._comm_stream is not None and self._done:
+                self._ship(lo, hi)
+            else:
+                works.append(_avg_all_reduce(self.arena.flat[lo:hi], async_op=cuda, group=self._group))
         works += self._pending
         self._pending = []
+        self._done = []
+        self._bwd_seen = {}
         for enc in self.encoders:
-            if id(enc) not in self._reduced:      # not already reduced chunk-wise during backward
-                works.append(_avg_all_reduce(enc.grad_arena(), async_op=True, group=self._group))
-        self._reduced = set()
-        # parameters outside the arena (tied weights appear once: parameters() de-duplicates)
-        others = [p for p in self.model.parameters() if p.grad is not None and id(p) not in arena_ids]
-        if others:
-            grads = [p.grad for p in others]
-            n = sum(g.numel() for g in grads)
-            if self._flat is None or self._flat.numel() != n or self._flat.dtype != grads[0].dtype:
-                self._flat = torch.empty(n, device=grads[0].device, dtype=grads[0].dtype)
-            views = list(self._flat.split([g.numel() for g in grads]))
-            torch._foreach_copy_(views, [g.reshape(-1) for g in grads])
-            w = _avg_all_reduce(self._flat, async_op=True)
-            if w is not None:
-                w.wait()
-            torch._foreach_copy_([g.view(-1) for g in grads], views)
+            enc._fwd_since_reduce = 0
         for w in works:
             if w is not None:
                 w.wait()
 
     def backward_and_reduce(self, loss):
-        """loss.backward() with the encoder gradients all-reduced chunk by chunk while the rest of
-        the backward is still running (replaces the non-overlapped Horovod call of
-        train_vqa.py:193-199), then the remaining parameters."""
+        """loss.backward() with the gradients all-reduced slice by slice while the rest of the
+        backward is still running (replaces the non-overlapped Horovod call of
+        train_vqa.py:193-199), then the remaining slices."""
         overlap = self.overlap_chunks > 1 and dist.get_backend() == "nccl"
         if overlap:
             for enc in self.encoders:

@@ -1,0 +1,173 @@
+"""Host-free training step: forward + backward (+ gradient exchange, + optimizer) replayed from a
+CUDA graph per batch-shape bucket.
+
+Why.  At the reference's batch sizes one step is a few milliseconds of GPU work spread over ~250
+kernels; enqueueing them from Python (autograd glue, ctypes marshalling, allocator) costs about as
+much host time as the GPU needs to run them, so the step is host-bound (the
+thing replaced is the per-op Python of model/layer.py:159-170 and the training loop around it,
+train_vqa.py:183-229).  A captured graph is enqueued with ONE driver call.
+
+What makes the step capturable here:
+  * every kernel of libub200 takes shapes from host-known lengths (`register_lengths`), never
+    from data on the device, and launches on the capturing stream;
+  * dropout streams are offset by a DEVICE counter (`rng_offset_dev`) that the graph itself bumps
+    at the start of every replay, so replays draw fresh masks;
+  * every parameter's .grad is a fixed view of the gradient arena (uniter_b200.arena): the kernels
+    write into the same addresses in every graph, whatever the bucket;
+  * the token count is padded to a bucket (`token_bucket`, default 128 rows = one GEMM row tile) with
+    ONE dummy sequence (see model._prefix_pack_host): identical results, bit for bit, and one graph
+    serves every batch of the bucket.  The key of a graph is
+    (tensor shapes of the batch, padded token count, attention max-seqlen bucket, accumulate flag).
+
+Usage:
+    step = GraphedStep(model, lambda b: model(b).sum() * b["mlm_inv_n"])
+    loss = step(host_batch, lens)          # host_batch: dict of (pinned) CPU tensors; lens: per-sample
+                                           # valid lengths of host_batch["attn_masks"] (prefix masks)
+`loss` is a static device tensor, overwritten by the next call of the same bucket.
+"""
+import numpy as np
+import torch
+
+from . import model as _model
+from .arena import GradArena
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class _Bucket(object):
+    __slots__ = ("graph", "inputs", "meta_dev", "meta_offs", "loss", "T_pad", "maxseq", "n_replays",
+                 "launches")
+
+
+class GraphedStep(object):
+    def __init__(self, module, loss_fn, token_bucket=128, reducer=None, optimizer=None,
+                 optimizer_kwargs=None, zero_all_grads=False, mask_key="attn_masks", warmup=2):
+        """module: the root nn.Module (its parameters' gradients go to one arena);
+        loss_fn(batch_on_device) -> scalar loss (runs the forward);
+        reducer: optional GradientReducer — its all-reduces are captured inside the graph, overlapped
+        with the backward exactly as in eager mode; optimizer: optional FusedAdamW stepped inside the
+        graph; zero_all_grads: see GradArena.begin_step(zero_all=...)."""
+        self.module = module
+        self.loss_fn = loss_fn
+        self.token_bucket = int(token_bucket)
+        self.reducer = reducer
+        self.optimizer = optimizer
+        self.optimizer_kwargs = optimizer_kwargs or {}
+        self.zero_all = bool(zero_all_grads)
+        self.mask_key = mask_key
+        self.warmup = int(warmup)
+        self.arena = GradArena.attach(module)
+        self.device = self.arena.device
+        self.buckets = {}
+        self.pool = None
+        self.rng_counter = torch.zeros(1, device=self.device, dtype=torch.int64)
+        self._meta_pinned = {}
+        self.captures = 0
+
+    # ------------------------------------------------------------------ keys / buffers
+    def _key(self, host_batch, lens, accumulate):
+        T = int(sum(lens))
+        T_pad = max(_round_up(T, self.token_bucket), self.token_bucket)
+        maxseq = _round_up(max(max(lens), 1, T_pad - T), 128)
+        sig = tuple((k, tuple(v.shape), str(v.dtype)) for k, v in sorted(host_batch.items())
+                    if torch.is_tensor(v))
+        return (sig, T_pad, maxseq, bool(accumulate)), T_pad, maxseq
+
+    def _fill_meta(self, bk, lens, L):
+        """Packing bookkeeping of this batch -> the bucket's static device buffer (one H2D)."""
+        host, offs, _ = _model._prefix_pack_host(lens, L, bk.T_pad)
+        n = host.numel()
+        slot = self._meta_pinned.get(n)
+        if slot is None:
+            slot = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(4)] + [0]
+            self._meta_pinned[n] = slot
+        i = slot[4]
+        slot[4] = (i + 1) % 4
+        slot[i].copy_(host)
+        bk.meta_dev.copy_(slot[i], non_blocking=True)
+        return offs
+
+    # ------------------------------------------------------------------ the captured region
+    def _run(self, bk, accumulate):
+        self.rng_counter.add_(64)                       # fresh dropout masks for this replay
+        self.arena.begin_step(accumulate=accumulate, zero_all=self.zero_all)
+        _model._RNG_GRAPH["dev"] = self.rng_counter
+        _model._RNG_GRAPH["call"] = 0
+        try:
+            loss = self.loss_fn(bk.inputs)
+            if self.reducer is not None:
+                self.reducer.backward_and_reduce(loss)
+            else:
+                loss.backward()
+            if self.optimizer is not None:
+                self.optimizer.step(**self.optimizer_kwargs)
+        finally:
+            _model._RNG_GRAPH["dev"] = None
+            self.arena.end_step_mode()
+        return loss.detach()
+
+    def _capture(self, key, host_batch, lens, T_pad, maxseq, accumulate):
+        bk = _Bucket()
+        bk.T_pad, bk.maxseq, bk.n_replays = T_pad, maxseq, 0
+        dev = self.device
+        bk.inputs = {k: torch.empty(v.shape, dtype=v.dtype, device=dev)
+                     for k, v in host_batch.items() if torch.is_tensor(v)}
+        for k, v in host_batch.items():
+            if torch.is_tensor(v):
+                bk.inputs[k].copy_(v, non_blocking=True)
+        mask = bk.inputs[self.mask_key]
+        B, L = mask.shape
+        host, offs, _ = _model._prefix_pack_host(lens, L, T_pad)
+        bk.meta_dev = torch.empty(host.numel(), dtype=torch.int32, device=dev)
+        bk.meta_offs = self._fill_meta(bk, lens, L)
+        meta = _model._meta_from_buffer(bk.meta_dev, bk.meta_offs, B, L, T_pad, maxseq, None, True)
+        _model._meta_store(mask, meta)            # forward() finds the static bookkeeping on this tensor
+        # warm-up on a side stream (allocator, cudaFuncSetAttribute, TMA descriptor cache), then capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(self.warmup):
+                self._run(bk, accumulate)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        if self.pool is None:
+            self.pool = torch.cuda.graph_pool_handle()
+        from . import _lib
+        lib = _lib.load()
+        lib.ub200_launch_count.restype = __import__("ctypes").c_ulonglong
+        n0 = lib.ub200_launch_count()
+        with torch.cuda.graph(g, pool=self.pool):
+            bk.loss = self._run(bk, accumulate)
+        bk.launches = int(lib.ub200_launch_count() - n0)     # libub200 kernels inside one replay
+        bk.graph = g
+        self.buckets[key] = bk
+        self.captures += 1
+        return bk
+
+    # ------------------------------------------------------------------ public
+    def stage(self, host_batch, lens, accumulate=False):
+        """Copy a host batch into its bucket's static inputs (async, current stream) and return the
+        bucket; capture the bucket's graph first if it is new."""
+        key, T_pad, maxseq = self._key(host_batch, lens, accumulate)
+        bk = self.buckets.get(key)
+        if bk is None:
+            bk = self._capture(key, host_batch, lens, T_pad, maxseq, accumulate)
+        for k, v in host_batch.items():
+            if torch.is_tensor(v):
+                bk.inputs[k].copy_(v, non_blocking=True)
+        mask = bk.inputs[self.mask_key]
+        self._fill_meta(bk, lens, mask.size(1))
+        return bk
+
+    def stage_from_device(self, dev_batch, lens, accumulate=False):
+        """Like stage(), but the tensors already sit in device memory (e.g. prefetched on a copy
+        stream): device-to-device copies into the static inputs."""
+        return self.stage(dev_batch, lens, accumulate)
+
+    def __call__(self, batch, lens, accumulate=False):
+        bk = self.stage(batch, lens, accumulate)
+        bk.graph.replay()
+        bk.n_replays += 1
+        return bk.loss

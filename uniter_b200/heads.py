@@ -67,10 +67,18 @@ _PAD_LOGIT = -30000.0   # finite in fp16 and bf16; exp(pad - max) underflows to 
 
 class _MlmHead(torch.autograd.Function):
     """scores = decoder(LayerNorm(gelu(dense(h)))) + bias ; loss = cross_entropy(scores, targets)
-    on libub200.  Returns the per-row loss (fp32) or, with ``want_scores``, the [n, V] scores."""
+    on libub200.  Returns the per-row loss (fp32) or, with ``want_scores``, the [n, V] scores.
+    Rows whose target is outside [0, V) (padding of a fixed-size index list) get loss 0 and
+    contribute no gradient.  The head's parameters are read by pointer and their gradients are
+    written straight into the gradient arena (the tied decoder / word-embedding gradient is one
+    buffer that the decoder wgrad writes first and the embedding scatter adds to later)."""
 
     @staticmethod
-    def forward(ctx, h, dense_w, dense_b, ln_g, ln_b, word_w, dec_bias, targets, want_scores):
+    def forward(ctx, h, module, targets, want_scores):
+        p = module.cls.predictions
+        dense_w, dense_b = p.transform.dense.weight, p.transform.dense.bias
+        ln_g, ln_b = p.transform.LayerNorm.weight, p.transform.LayerNorm.bias
+        word_w, dec_bias = p.decoder.weight, p.bias
         n, H = h.shape
         V = word_w.size(0)
         Vp = (V + 7) // 8 * 8
@@ -90,29 +98,41 @@ class _MlmHead(torch.autograd.Function):
             return scores
         targets = targets.contiguous()
         loss, lse = ops.ce_fwd(logits, targets, V)                    # model/pretrain.py:122-125
-        ctx.save_for_backward(h, pre, t, z, logits, lse, targets, dense_w, ln_g, word_w)
+        ctx.save_for_backward(h, pre, t, z, logits, lse, targets)
         ctx.V = V
+        ctx.module = module
         return loss
 
     @staticmethod
     def backward(ctx, dloss):
-        h, pre, t, z, logits, lse, targets, dense_w, ln_g, word_w = ctx.saved_tensors
+        from .arena import GradArena
+        h, pre, t, z, logits, lse, targets = ctx.saved_tensors
+        module = ctx.module
+        p = module.cls.predictions
+        dense_w, dense_b = p.transform.dense.weight, p.transform.dense.bias
+        ln_g, ln_b = p.transform.LayerNorm.weight, p.transform.LayerNorm.bias
+        word_w, dec_bias = p.decoder.weight, p.bias
+        arena = GradArena.for_params(module, dense_w)
+        arena.mark_managed([dense_w, dense_b, ln_g, ln_b, dec_bias])
         V = ctx.V
         dtype = h.dtype
         # the scores are dead after this point: the gradient overwrites them
         dlog = ops.ce_bwd_(logits, targets, lse, dloss.contiguous().float(), V)
-        d_dec_bias = ops.cvt_from_f32(ops.colsum(dlog)[:V], dtype)
         dlv = dlog[:, :V]                                             # [n, V], row pitch Vp
         # dz = dlog W_dec: 2 x (H / 128) output tiles, K = V -> split-K over the SMs (fp32 atomics)
         dz = ops.cvt_from_f32(ops.gemm(dlv, word_w, b_major=1, k_splits=-1), dtype)
-        d_word = ops.gemm(dlv, z, a_major=1, b_major=1)               # [V, H] = dlog^T z
+        acc = arena.claim([word_w])
+        ops.gemm(dlv, z, a_major=1, b_major=1, out=arena.view(word_w), accumulate=acc)   # [V, H] = dlog^T z
         dt, _, dg, db, _ = ops.layernorm_bwd(dz, t, ln_g, want_dbias=False)
         dpre = ops.dgelu_mul(dt, pre)
         dh = ops.gemm(dpre, dense_w, b_major=1)
-        d_dense_w = ops.gemm(dpre, h, a_major=1, b_major=1)
-        d_dense_b = ops.cvt_from_f32(ops.colsum(dpre), dtype)
-        return (dh, d_dense_w, d_dense_b, ops.cvt_from_f32(dg, dtype), ops.cvt_from_f32(db, dtype),
-                d_word, d_dec_bias, None, None)
+        acc = arena.claim([dense_w, dense_b, ln_g, ln_b, dec_bias])
+        ops.gemm(dpre, h, a_major=1, b_major=1, out=arena.view(dense_w), accumulate=acc)
+        ops.cvt_from_f32(ops.colsum(dpre), dtype, out=arena.view(dense_b), accumulate=acc)
+        ops.cvt_from_f32(dg, dtype, out=arena.view(ln_g), accumulate=acc)
+        ops.cvt_from_f32(db, dtype, out=arena.view(ln_b), accumulate=acc)
+        ops.cvt_from_f32(ops.colsum(dlog)[:V], dtype, out=arena.view(dec_bias), accumulate=acc)
+        return dh, None, None, None
 
 
 class UniterForMLM(UniterPreTrainedModel):
@@ -125,6 +145,10 @@ class UniterForMLM(UniterPreTrainedModel):
         self.apply(self.init_weights)
 
     def forward(self, batch, compute_loss=True):
+        """Per-masked-token loss [n] (fp32), or the scores [n, V].  With loader-provided
+        `mlm_index` (flat positions b * L + j; entries equal to B * L and targets of -1 are PADDING
+        of a fixed-size list: zero rows, zero loss, no gradient) nothing here depends on data on
+        the device, so the step can be captured in a CUDA graph."""
         batch = defaultdict(lambda: None, batch)
         input_ids = batch["input_ids"]
         packed, meta = self.uniter.encode_packed(
@@ -144,12 +168,9 @@ class UniterForMLM(UniterPreTrainedModel):
         if flat.numel() == 0:
             V = self.uniter.config.vocab_size
             return packed.new_zeros(0, dtype=torch.float32) if compute_loss else packed.new_zeros(0, V)
-        rows = meta["unpack_idx"][flat]                                # packed row of each masked token
+        rows = meta["unpack_ext"][flat]                                # packed row of each masked token
         masked_output = gather_packed_rows(packed, rows)               # [n, H]
-        p = self.cls.predictions
-        return _MlmHead.apply(masked_output, p.transform.dense.weight, p.transform.dense.bias,
-                              p.transform.LayerNorm.weight, p.transform.LayerNorm.bias,
-                              p.decoder.weight, p.bias, targets, not compute_loss)
+        return _MlmHead.apply(masked_output, self, targets, not compute_loss)
 
 
 class UniterForVisualQuestionAnswering(UniterPreTrainedModel):

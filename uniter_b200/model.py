@@ -286,7 +286,7 @@ class _EncoderDesc(C.Structure):
                 ("total_tokens", C.c_int32), ("max_seqlen", C.c_int32),
                 ("cu_seqlens", C.c_void_p), ("hidden_dropout_p", C.c_float),
                 ("attn_dropout_p", C.c_float), ("rng_seed", C.c_uint64), ("rng_offset", C.c_uint64),
-                ("layer_offset", C.c_int32)]
+                ("layer_offset", C.c_int32), ("rng_offset_dev", C.c_void_p)]
 
 
 _lib_ready = False
@@ -317,6 +317,23 @@ def _bind():
 
 
 _rng_offset = [0]
+# Graph mode (uniter_b200.graphed.GraphedStep): the host-side offset of a launch is frozen inside a
+# captured CUDA graph, so the per-step part of the dropout stream id comes from a DEVICE counter
+# (bumped inside the graph at the start of every replay) and the host only numbers the calls
+# within one step.
+_RNG_GRAPH = {"dev": None, "call": 0}
+
+
+def _next_rng(device):
+    """(seed, host offset, device-counter pointer or None) for one forward call that draws dropout."""
+    seed = torch.cuda.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    if _RNG_GRAPH["dev"] is not None:
+        _RNG_GRAPH["call"] += 1
+        return seed, _RNG_GRAPH["call"], _RNG_GRAPH["dev"].data_ptr()
+    _rng_offset[0] += 1
+    return seed, _rng_offset[0], None
+
+
 _META_CACHE = {}
 _META_RING = _lib.PinnedRing(8)
 
@@ -344,26 +361,54 @@ def _meta_store(t, meta):
     _META_CACHE[id(t)] = (weakref.ref(t), _meta_key(t), meta)
 
 
-def _prefix_pack_host(lens, L):
+def _prefix_pack_host(lens, L, T_pad=None):
     """Packing bookkeeping of a batch of PREFIX masks ([1]*S_b + [0]*(L-S_b)) from the host-known
-    lengths: one int32 buffer holding cu_seqlens [B+1], pack_idx [T] (packed row -> b*L+j) and
-    unpack_idx [B*L] (b*L+j -> packed row, -1 at masked positions); sections start on 16-byte
-    boundaries.  Returns (buffer, (offset_cu, offset_pack, offset_unpack))."""
+    lengths, as ONE int32 buffer (sections start on 16-byte boundaries):
+
+        cu_seqlens [B+2]   row range of sequence b; entry B+1 closes a DUMMY sequence (see below)
+        pack_idx   [T_pad] packed row -> flat position b*L+j it is computed from
+        pack_inv   [T_pad] the same, but -1 on dummy rows (inverse map for gradients)
+        unpack_idx [B*L+1] flat position -> packed row, -1 at masked positions; the extra last entry
+                           is -1 so that index B*L means "no row" (padding of index lists)
+
+    `T_pad` > T (graph mode) pads the token count to a bucket size with one DUMMY sequence of
+    T_pad - T rows after the real ones, so that a captured CUDA graph (whose launch shapes are
+    frozen) serves every batch of the bucket.  Dummy rows are computed from the first valid position
+    (finite values), attend only to each other, are referenced by no output position and receive a
+    zero gradient, so they change neither the loss nor any gradient — bit for bit.
+    Returns (buffer, offsets dict, T)."""
     B = len(lens)
     lens_a = np.asarray(lens, dtype=np.int64).reshape(B)
-    cu = np.zeros(B + 1, dtype=np.int64)
-    np.cumsum(lens_a, out=cu[1:])
-    T = int(cu[-1])
+    cu = np.zeros(B + 2, dtype=np.int64)
+    np.cumsum(lens_a, out=cu[1:B + 1])
+    T = int(cu[B])
+    T_pad = T if T_pad is None else int(T_pad)
+    assert T_pad >= T
+    cu[B + 1] = T_pad
     row_b = np.repeat(np.arange(B, dtype=np.int64), lens_a)     # (torch.repeat_interleave on CPU
     pack = np.arange(T, dtype=np.int64) - cu[row_b] + row_b * L  #  costs ~20 ms here; numpy ~20 us)
-    o_pack = (B + 1 + 3) // 4 * 4
-    o_unpack = o_pack + (T + 3) // 4 * 4
-    buf = np.full(o_unpack + B * L, -1, dtype=np.int32)
-    buf[:B + 1] = cu
+    o_pack = (B + 2 + 3) // 4 * 4
+    o_inv = o_pack + (T_pad + 3) // 4 * 4
+    o_unpack = o_inv + (T_pad + 3) // 4 * 4
+    buf = np.full(o_unpack + B * L + 1, -1, dtype=np.int32)
+    buf[:B + 2] = cu
     buf[o_pack:o_pack + T] = pack
+    buf[o_pack + T:o_pack + T_pad] = pack[0] if T else 0
+    buf[o_inv:o_inv + T] = pack
     buf[o_unpack + pack] = np.arange(T, dtype=np.int32)
     host = torch.from_numpy(buf)
-    return host, (0, o_pack, o_unpack)
+    return host, dict(cu=0, pack=o_pack, inv=o_inv, unpack=o_unpack, size=buf.size), T
+
+
+def _meta_from_buffer(devbuf, offs, B, L, T_pad, max_seqlen, lens_host, dummy):
+    """Meta dict over a device copy of the _prefix_pack_host buffer."""
+    return dict(batch=B + 1 if dummy else B, L=L, total=T_pad, max_seqlen=max_seqlen,
+                cu_seqlens=devbuf[offs["cu"]:offs["cu"] + B + 2],
+                pack_idx=devbuf[offs["pack"]:offs["pack"] + T_pad],
+                pack_inv=devbuf[offs["inv"]:offs["inv"] + T_pad],
+                unpack_idx=devbuf[offs["unpack"]:offs["unpack"] + B * L],
+                unpack_ext=devbuf[offs["unpack"]:offs["unpack"] + B * L + 1],
+                lens_host=lens_host, n_batch=B)
 
 
 def register_lengths(attention_mask_dev, lens_host, prefix=False):
@@ -420,15 +465,20 @@ class _GatherRows(torch.autograd.Function):
 class _EmbedFront(torch.autograd.Function):
     """Embedding front-end straight into packed rows (model/model.py:217-334) on libub200:
     ub200_embed_prep -> ub200_embed_gather_cast -> ub200_gemm (img_linear) -> ub200_embed_rows_fwd.
-    Backward: row-kind masked ub200_layernorm_bwd x4, wgrad GEMM for img_linear, table scatter."""
+    Backward: row-kind masked ub200_layernorm_bwd x4, wgrad GEMM for img_linear, table scatter.
+
+    The parameters are NOT autograd inputs: the kernels read them by pointer and the backward writes
+    their gradients straight into the model's gradient arena (uniter_b200.arena) — `anchor` is the
+    requires-grad handle that makes autograd call backward."""
 
     @staticmethod
-    def forward(ctx, model, meta, mode, input_ids, position_ids, img_feat, img_pos_feat, gather_index,
-                img_masks, txt_type_ids, img_type_ids, dropout_p,
-                word_w, pos_w, type_w, lnt_g, lnt_b, img_w, img_b, lni_g, lni_b, lnp_g, lnp_b,
-                posl_w, posl_b, mask_w, lnf_g, lnf_b):
+    def forward(ctx, anchor, model, meta, mode, input_ids, position_ids, img_feat, img_pos_feat,
+                gather_index, img_masks, txt_type_ids, img_type_ids, dropout_p):
         from . import ops
         lib = _bind()
+        te, ie = model.embeddings, model.img_embeddings
+        word_w, pos_w, type_w = (te.word_embeddings.weight, te.position_embeddings.weight,
+                                 te.token_type_embeddings.weight)
         T, L = meta["total"], meta["L"]
         dev, dtype = word_w.device, word_w.dtype
         H = word_w.size(1)
@@ -460,45 +510,49 @@ class _EmbedFront(torch.autograd.Function):
             img_feat = img_feat.contiguous()
             D = img_feat.size(-1)
             A = torch.empty(T, D, device=dev, dtype=dtype)
-            mask_row = mask_w[1].contiguous()
+            mask_row = ie.mask_embedding.weight[1].contiguous()
             _lib.check(lib.ub200_embed_gather_cast(
                 img_feat.data_ptr(), 1 if img_feat.dtype == torch.float32 else 0, idx[4].data_ptr(),
                 idx[5].data_ptr(), mask_row.data_ptr(), A.data_ptr(), T, D, dt, stream))
-            G = ops.gemm(A, img_w, bias=img_b)                       # img_linear on the tcgen05 core
+            G = ops.gemm(A, ie.img_linear.weight, bias=ie.img_linear.bias)   # img_linear on the tcgen05 core
             pos_feat = img_pos_feat.float().contiguous().view(-1, img_pos_feat.size(-1))
             assert pos_feat.size(1) == 7
         x = torch.empty(T, H, device=dev, dtype=dtype)
         u = torch.empty_like(x)
         ppre = torch.empty_like(x)
-        _rng_offset[0] += 1
-        seed = torch.cuda.initial_seed() & 0xFFFFFFFFFFFFFFFF
-        rng_stream = (_rng_offset[0] << 20) | (0xFFFF << 4) | 4
+        seed, offset, rng_dev = _next_rng(dev)
+        rng_stream = (offset << 20) | (0xFFFF << 4) | 4
         r = _lib.EmbedRowsArgs(
             kind=idx[0].data_ptr(), word_id=idx[1].data_ptr(), pos_id=idx[2].data_ptr(),
             type_id=idx[3].data_ptr(), img_src=idx[4].data_ptr(),
             word_emb=word_w.data_ptr(), pos_emb=pos_w.data_ptr(), type_emb=type_w.data_ptr(),
-            ln_txt_g=lnt_g.data_ptr(), ln_txt_b=lnt_b.data_ptr(),
+            ln_txt_g=te.LayerNorm.weight.data_ptr(), ln_txt_b=te.LayerNorm.bias.data_ptr(),
             img_linear_out=_lib.ptr(G), pos_feat=_lib.ptr(pos_feat),
-            w_pos=posl_w.contiguous().data_ptr(), b_pos=posl_b.data_ptr(),
-            ln_img_g=lni_g.data_ptr(), ln_img_b=lni_b.data_ptr(), ln_pos_g=lnp_g.data_ptr(),
-            ln_pos_b=lnp_b.data_ptr(), ln_out_g=lnf_g.data_ptr(), ln_out_b=lnf_b.data_ptr(),
+            w_pos=ie.pos_linear.weight.contiguous().data_ptr(), b_pos=ie.pos_linear.bias.data_ptr(),
+            ln_img_g=ie.img_layer_norm.weight.data_ptr(), ln_img_b=ie.img_layer_norm.bias.data_ptr(),
+            ln_pos_g=ie.pos_layer_norm.weight.data_ptr(), ln_pos_b=ie.pos_layer_norm.bias.data_ptr(),
+            ln_out_g=ie.LayerNorm.weight.data_ptr(), ln_out_b=ie.LayerNorm.bias.data_ptr(),
             x=x.data_ptr(), u=u.data_ptr(), ppre=ppre.data_ptr(), T=T, hidden=H, dtype=dt,
-            dropout_p=float(dropout_p), rng_seed=seed, rng_stream=rng_stream)
+            dropout_p=float(dropout_p), rng_seed=seed, rng_stream=rng_stream, rng_offset_dev=rng_dev)
         _lib.check(lib.ub200_embed_rows_fwd(C.byref(r), stream))
-        ctx.mode, ctx.dropout_p, ctx.seed, ctx.rng_stream = mode, float(dropout_p), seed, rng_stream
+        ctx.model = model
+        ctx.mode, ctx.dropout_p, ctx.seed, ctx.rng_stream, ctx.rng_dev = mode, float(dropout_p), seed, rng_stream, rng_dev
         ctx.has_masks = img_masks is not None
-        ctx.shapes = (word_w.shape, pos_w.shape, type_w.shape, posl_w.shape, mask_w.shape)
-        ctx.save_for_backward(idx, A, G, u, ppre, pos_feat, lnt_g, lni_g, lnp_g, lnf_g, img_w)
+        ctx.save_for_backward(idx, A, G, u, ppre, pos_feat)
         return x
 
     @staticmethod
     def backward(ctx, dx):
         """Row-kind masked LayerNorm backward (x4), img_linear wgrad on the tcgen05 GEMM, then the
         table gradients in three launches (ub200_embed_bwd_scatter / _colsums); every small fp32
-        gradient lives in ONE staging buffer that is converted to the model dtype by one launch."""
+        gradient lives in ONE staging buffer whose layout equals the arena's front-end small section,
+        so one launch converts (or accumulates) all of them into the parameters' .grad views."""
         from . import ops
         lib = _bind()
-        idx, A, G, u, ppre, pos_feat, lnt_g, lni_g, lnp_g, lnf_g, img_w = ctx.saved_tensors
+        model = ctx.model
+        idx, A, G, u, ppre, pos_feat = ctx.saved_tensors
+        te, ie = model.embeddings, model.img_embeddings
+        arena, ep = model._ensure_arena()
         dx = dx.contiguous()
         T, H = dx.shape
         dtype, dev = dx.dtype, dx.device
@@ -506,74 +560,73 @@ class _EmbedFront(torch.autograd.Function):
         stream = _lib.current_stream()
         kind, word_id, pos_id, type_id, img_src, mask_flag = (idx[i] for i in range(6))
         kw = dict(dropout_p=ctx.dropout_p, rng_seed=ctx.seed, rng_stream=ctx.rng_stream,
-                  row_kind=kind, dropout_on_dy=ctx.dropout_p > 0)
-        word_shape, pos_shape, type_shape, posl_shape, mask_shape = ctx.shapes
+                  row_kind=kind, dropout_on_dy=ctx.dropout_p > 0, rng_offset_dev=ctx.rng_dev)
         has_txt, has_img = ctx.mode != 2, ctx.mode != 1
         # ---- one fp32 staging buffer for every small gradient (accumulated by the kernels)
-        n_pos = pos_shape[0] * H if has_txt else 0
-        n_type = type_shape[0] * H
-        names = ["lnt_g", "lnt_b", "lnf_g", "lnf_b", "lni_g", "lni_b", "lnp_g", "lnp_b", "img_b", "posl_b"]
-        sizes = [n_pos, n_type] + [H] * len(names) + [H * 7]
-        offs = [0]
-        for n in sizes:
-            offs.append(offs[-1] + n)
-        S = torch.zeros(offs[-1], device=dev, dtype=torch.float32)
-        sec = {"pos": S[offs[0]:offs[1]], "type": S[offs[1]:offs[2]]}
-        for i, nme in enumerate(names):
-            sec[nme] = S[offs[2 + i]:offs[3 + i]]
-        sec["posl_w"] = S[offs[-2]:offs[-1]]
+        fs = ep["front_small"]                      # name -> (offset, numel) inside the small section
+        S = torch.zeros(ep["front_small_n"], device=dev, dtype=torch.float32)
+        sec = {k: S[o:o + n] for k, (o, n) in fs.items()}
 
         du = torch.empty_like(dx)        # every packed row is text or image: fully written below
         if has_txt:
-            ops.layernorm_bwd(dx, u, lnt_g, kind=0, dx=du, want_dbias=False,
+            ops.layernorm_bwd(dx, u, te.LayerNorm.weight, kind=0, dx=du, want_dbias=False,
                               dgamma=sec["lnt_g"], dbeta=sec["lnt_b"], **kw)
         if has_img:
-            ops.layernorm_bwd(dx, u, lnf_g, kind=1, dx=du, want_dbias=False,
+            ops.layernorm_bwd(dx, u, ie.LayerNorm.weight, kind=1, dx=du, want_dbias=False,
                               dgamma=sec["lnf_g"], dbeta=sec["lnf_b"], **kw)
-        d_word = None
         if has_txt:
-            d_word = torch.zeros(word_shape, device=dev, dtype=dtype)
+            word = te.word_embeddings.weight
+            d_word = arena.view(word)
+            if not arena.claim([word]):      # first writer of this step: the scatter is additive
+                d_word.zero_()
             _lib.check(lib.ub200_embed_bwd_scatter(du.data_ptr(), kind.data_ptr(), word_id.data_ptr(),
                                                    pos_id.data_ptr(), d_word.data_ptr(),
                                                    sec["pos"].data_ptr(), T, H, dt, stream))
+        type_w = te.token_type_embeddings.weight
         ca = _lib.EmbedColsumArgs(x=du.data_ptr(), type_id=type_id.data_ptr(), out=sec["type"].data_ptr(),
-                                  T=T, hidden=H, mode=0, type_vocab=type_shape[0], dtype=dt)
+                                  T=T, hidden=H, mode=0, type_vocab=type_w.size(0), dtype=dt)
         _lib.check(lib.ub200_embed_bwd_colsums(C.byref(ca), stream))
-        d_img_w = d_mask = None
         if has_img:
             dG = torch.empty_like(dx)    # text rows are zeroed by the kernel (zero_inactive)
             dP = torch.empty_like(dx)
-            ops.layernorm_bwd(du, G, lni_g, row_kind=kind, kind=1, dx=dG, zero_inactive=True,
+            ops.layernorm_bwd(du, G, ie.img_layer_norm.weight, row_kind=kind, kind=1, dx=dG, zero_inactive=True,
                               dgamma=sec["lni_g"], dbeta=sec["lni_b"], dbias=sec["img_b"])
-            ops.layernorm_bwd(du, ppre, lnp_g, row_kind=kind, kind=1, dx=dP, zero_inactive=True,
+            ops.layernorm_bwd(du, ppre, ie.pos_layer_norm.weight, row_kind=kind, kind=1, dx=dP, zero_inactive=True,
                               dgamma=sec["lnp_g"], dbeta=sec["lnp_b"], dbias=sec["posl_b"])
             # img_linear.weight [H, D] = dG^T A   (wgrad form: both operands read un-transposed)
-            d_img_w = ops.gemm(dG, A, a_major=1, b_major=1)
+            img_w = ie.img_linear.weight
+            acc = arena.claim([img_w])
+            ops.gemm(dG, A, a_major=1, b_major=1, out=arena.view(img_w), accumulate=acc)
             # pos_linear.weight [H, 7] = dP^T box  (K = T reduction with 7 weights per row)
             ca = _lib.EmbedColsumArgs(x=dP.data_ptr(), kind=kind.data_ptr(), img_src=img_src.data_ptr(),
                                       pos_feat=pos_feat.data_ptr(), out=sec["posl_w"].data_ptr(),
                                       T=T, hidden=H, mode=1, type_vocab=0, dtype=dt)
             _lib.check(lib.ub200_embed_bwd_colsums(C.byref(ca), stream))
-            if ctx.has_masks and ctx.needs_input_grad[25]:
+            mask_w = ie.mask_embedding.weight
+            if ctx.has_masks and mask_w.requires_grad:
                 dA = ops.gemm(dG, img_w, b_major=1)                                 # [T, D]
-                d_mask = torch.zeros(mask_shape, device=dev, dtype=dtype)
-                d_mask[1] = (dA.float() * (mask_flag != 0).unsqueeze(1)).sum(0).to(dtype)
-        # ---- fp32 -> model dtype, one launch; the returned gradients are views of S16
-        S16 = torch.empty(offs[-1], device=dev, dtype=dtype)
-        _lib.check(lib.ub200_cvt_from_f32_strided(S.data_ptr(), S16.data_ptr(), offs[-1], 1, 0, 0, 0, dt,
-                                                  stream))
-        g16 = {"pos": S16[offs[0]:offs[1]].view(pos_shape) if has_txt else None,
-               "type": S16[offs[1]:offs[2]].view(type_shape)}
-        for i, nme in enumerate(names):
-            g16[nme] = S16[offs[2 + i]:offs[3 + i]]
-        g16["posl_w"] = S16[offs[-2]:offs[-1]].view(posl_shape)
-        t_, i_ = has_txt, has_img
-        return (None,) * 12 + (
-            d_word, g16["pos"], g16["type"], g16["lnt_g"] if t_ else None, g16["lnt_b"] if t_ else None,
-            d_img_w, g16["img_b"] if i_ else None, g16["lni_g"] if i_ else None,
-            g16["lni_b"] if i_ else None, g16["lnp_g"] if i_ else None, g16["lnp_b"] if i_ else None,
-            g16["posl_w"] if i_ else None, g16["posl_b"] if i_ else None, d_mask,
-            g16["lnf_g"] if i_ else None, g16["lnf_b"] if i_ else None)
+                row = (dA.float() * (mask_flag != 0).unsqueeze(1)).sum(0).to(dtype)
+                d_mask = arena.view(mask_w)
+                if arena.claim([mask_w]):
+                    d_mask[1].add_(row)
+                else:
+                    d_mask.zero_()
+                    d_mask[1].copy_(row)
+        # ---- fp32 -> model dtype straight into the arena's small section, one launch.  The section is
+        # ordered [text-only | token_type | image-only], so the parameters a mode touches are one
+        # contiguous range (text-only: prefix, image-only: suffix) and the others are left alone.
+        names = ep["front_small_order"]
+        first = 0 if has_txt else names.index("type")
+        last = len(names) - 1 if has_img else names.index("type")
+        used = ep["front_small_params"][first:last + 1]
+        acc = arena.claim(used)
+        r_lo = fs[names[first]][0]
+        r_hi = fs[names[last]][0] + fs[names[last]][1]
+        lo, _ = ep["segments"]["front_small"]
+        dst = arena.flat[lo + r_lo:lo + r_hi]
+        _lib.check(lib.ub200_cvt_from_f32_strided(S[r_lo:].data_ptr(), dst.data_ptr(), r_hi - r_lo, 1, 0, 0,
+                                                  1 if acc else 0, dt, stream))
+        return (None,) * 13
 
 
 class _EncoderStack(torch.autograd.Function):
@@ -588,13 +641,13 @@ class _EncoderStack(torch.autograd.Function):
         training = model.training
         p_hidden = float(model.encoder.layer[0].output.dropout.p) if training else 0.0
         p_attn = float(model.encoder.layer[0].attention.self.dropout.p) if training else 0.0
-        _rng_offset[0] += 1
+        seed, offset, rng_dev = _next_rng(x.device)
         desc = _EncoderDesc(
             hidden=H, intermediate=cfg.intermediate_size, num_heads=cfg.num_attention_heads,
             num_layers=NL, dtype=_lib.dtype_code(x.dtype), batch=meta["batch"], total_tokens=T,
             max_seqlen=meta["max_seqlen"], cu_seqlens=meta["cu_seqlens"].data_ptr(),
             hidden_dropout_p=p_hidden, attn_dropout_p=p_attn,
-            rng_seed=torch.cuda.initial_seed() & 0xFFFFFFFFFFFFFFFF, rng_offset=_rng_offset[0])
+            rng_seed=seed, rng_offset=offset, rng_offset_dev=rng_dev)
         weights = model._weight_table()
         act_bytes = lib.ub200_encoder_act_bytes_per_layer(C.byref(desc))
         act = torch.empty((NL if need_grad else 1) * act_bytes, device=x.device, dtype=torch.uint8)
@@ -604,6 +657,8 @@ class _EncoderStack(torch.autograd.Function):
         _lib.check(lib.ub200_encoder_fwd(C.byref(desc), weights, x.data_ptr(), out_ptrs,
                                          act.data_ptr(), 1 if need_grad else 0,
                                          _lib.current_stream()))
+        if need_grad:
+            model._fwd_since_reduce = getattr(model, "_fwd_since_reduce", 0) + 1
         ctx.model = model
         ctx.desc = desc
         ctx.meta = meta
@@ -623,7 +678,9 @@ class _EncoderStack(torch.autograd.Function):
         NL = desc.num_layers
         T, H = x.shape
         grad_out = grad_out.contiguous()
-        grads, accumulate = model._grad_table()
+        arena, ep = model._ensure_arena()
+        grads = ep["gtable"]
+        ep["small32"].zero_()
         weights = model._weight_table()
         scratch = torch.empty(lib.ub200_encoder_bwd_scratch_bytes(C.byref(desc)), device=x.device,
                               dtype=torch.uint8)
@@ -638,6 +695,7 @@ class _EncoderStack(torch.autograd.Function):
         for ci in range(nchunks - 1, -1, -1):
             lo, hi = bounds[ci], bounds[ci + 1]
             n = hi - lo
+            accumulate = arena.claim([q for lp in ep["layer_params"][lo:hi] for q in lp])
             d = _EncoderDesc.from_buffer_copy(desc)
             d.num_layers, d.layer_offset = n, lo
             d_ptrs = (C.c_void_p * n)()
@@ -730,90 +788,132 @@ class UniterModel(UniterPreTrainedModel):
         self._wtable = table
         self._packed_key = tuple(l.attention.self.query.weight.data_ptr() for l in layers) + \
             tuple(l.output.dense.weight.data_ptr() for l in layers)
-        self._arena = None  # gradient arena must match the (possibly new) dtype / device
         return table
 
-    def _build_arena(self):
-        """Flat 16-bit gradient arena for all encoder-layer parameters (the unit of the NCCL
-        gradient allreduce) + fp32 accumulators for the small (bias / LayerNorm) gradients."""
+    # The gradient arena (uniter_b200.arena.GradArena) owns ONE flat buffer for every parameter of
+    # the root module it was attached to; the encoder contributes its library layout to the plan.
+    def _plan_arena(self, off):
+        """Element offsets of this model's parameters inside a GradArena starting at `off`."""
         lib = _bind()
         cfg = self.config
         H, I, NL = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
-        p0 = self.encoder.layer[0].attention.self.query.weight
+        plan, seg = [], {}
+
+        def put(p, o):
+            plan.append((p, o, p.numel()))
+
+        def a8(n):
+            return (n + 7) // 8 * 8
+        # ---- pooler (its backward runs before the encoder's)
+        lo = off
+        for p in self.pooler.parameters():
+            put(p, off)
+            off += a8(p.numel())
+        seg["pooler"] = (lo, off)
+        # ---- encoder layers, library layout (ub200_layer_grads)
         small_n = lib.ub200_encoder_small_grad_count(H, I)
         big_n = 3 * H * H + H * H + I * H + H * I
-        per_layer = big_n + small_n
-        flat = torch.zeros(NL * per_layer, device=p0.device, dtype=p0.dtype)
-        small32 = torch.zeros(NL * small_n, device=p0.device, dtype=torch.float32)
-        gtable = (_LayerGrads * NL)()
-        views = []  # (param, grad_view)
+        per_layer = a8(big_n + small_n)
+        layer0 = off
+        layer_params = []
         for i, layer in enumerate(self.encoder.layer):
             P = self._layer_params(layer)
-            base = i * per_layer
-            o = base
-            dwqkv = flat[o:o + 3 * H * H].view(3 * H, H); o += 3 * H * H
-            dwo = flat[o:o + H * H].view(H, H); o += H * H
-            dw1 = flat[o:o + I * H].view(I, H); o += I * H
-            dw2 = flat[o:o + H * I].view(H, I); o += H * I
-            small16 = flat[o:o + small_n]
-            views += [(P["q_w"], dwqkv[:H]), (P["k_w"], dwqkv[H:2 * H]), (P["v_w"], dwqkv[2 * H:]),
-                      (P["wo"], dwo), (P["w1"], dw1), (P["w2"], dw2)]
-            s = 0
+            o = layer0 + i * per_layer
+            put(P["q_w"], o); put(P["k_w"], o + H * H); put(P["v_w"], o + 2 * H * H); o += 3 * H * H
+            put(P["wo"], o); o += H * H
+            put(P["w1"], o); o += I * H
+            put(P["w2"], o); o += H * I
             for name, n in (("q_b", H), ("k_b", H), ("v_b", H), ("bo", H), ("ln1_g", H), ("ln1_b", H),
                             ("b1", I), ("b2", H), ("ln2_g", H), ("ln2_b", H)):
-                views.append((P[name], small16[s:s + n]))
-                s += n
+                put(P[name], o)
+                o += n
+            layer_params.append([P[k] for k in ("q_w", "k_w", "v_w", "wo", "w1", "w2", "q_b", "k_b", "v_b",
+                                                "bo", "ln1_g", "ln1_b", "b1", "b2", "ln2_g", "ln2_b")])
+        off = layer0 + NL * per_layer
+        seg["layers"] = (layer0, off)
+        # ---- embedding front-end: big tables, then the small section in staging-buffer order
+        te, ie = self.embeddings, self.img_embeddings
+        lo = off
+        for p in (te.word_embeddings.weight, ie.img_linear.weight, ie.mask_embedding.weight):
+            put(p, off)
+            off += a8(p.numel())
+        small_lo = off
+        order = [("pos", te.position_embeddings.weight), ("lnt_g", te.LayerNorm.weight),
+                 ("lnt_b", te.LayerNorm.bias), ("type", te.token_type_embeddings.weight),
+                 ("lnf_g", ie.LayerNorm.weight), ("lnf_b", ie.LayerNorm.bias),
+                 ("lni_g", ie.img_layer_norm.weight), ("lni_b", ie.img_layer_norm.bias),
+                 ("lnp_g", ie.pos_layer_norm.weight), ("lnp_b", ie.pos_layer_norm.bias),
+                 ("img_b", ie.img_linear.bias), ("posl_b", ie.pos_linear.bias),
+                 ("posl_w", ie.pos_linear.weight)]
+        front_small = {}
+        for name, p in order:       # H % 8 == 0 for every entry (H * 7 included): no padding inside
+            put(p, off)
+            front_small[name] = (off - small_lo, p.numel())
+            off += p.numel()
+        front_small_n = off - small_lo
+        off = a8(off)
+        seg["front"] = (lo, off)
+        seg["front_small"] = (small_lo, small_lo + front_small_n)
+        return dict(plan=plan, segments=seg, end=off, per_layer=per_layer, layer0=layer0, big_n=big_n,
+                    small_n=small_n, layer_params=layer_params, front_small=front_small,
+                    front_small_n=front_small_n, front_small_params=[p for _, p in order],
+                    front_small_order=[n for n, _ in order])
+
+    def _bind_arena(self, arena, ep):
+        """Called by GradArena once its flat buffer exists: pointer tables for the C ABI."""
+        NL = self.config.num_hidden_layers
+        H, I = self.config.hidden_size, self.config.intermediate_size
+        flat = arena.flat
+        es = flat.element_size()
+        small32 = torch.zeros(NL * ep["small_n"], device=flat.device, dtype=torch.float32)
+        gtable = (_LayerGrads * NL)()
+        for i in range(NL):
+            base = flat.data_ptr() + (ep["layer0"] + i * ep["per_layer"]) * es
             g = gtable[i]
-            g.dwqkv, g.dwo, g.dw1, g.dw2 = dwqkv.data_ptr(), dwo.data_ptr(), dw1.data_ptr(), dw2.data_ptr()
-            g.small = small32[i * small_n:(i + 1) * small_n].data_ptr()
-        self._arena = dict(flat=flat, small32=small32, gtable=gtable, views=views, small_n=small_n,
-                           per_layer=per_layer, big_n=big_n)
+            g.dwqkv = base
+            g.dwo = base + 3 * H * H * es
+            g.dw1 = g.dwo + H * H * es
+            g.dw2 = g.dw1 + I * H * es
+            g.small = small32[i * ep["small_n"]:(i + 1) * ep["small_n"]].data_ptr()
+        ep["gtable"], ep["small32"] = gtable, small32
+        te, ie = self.embeddings, self.img_embeddings
+        managed = [q for lp in ep["layer_params"] for q in lp] + ep["front_small_params"] + \
+            [te.word_embeddings.weight, ie.img_linear.weight, ie.mask_embedding.weight]
+        arena.mark_managed(managed)
+        self._arena = (arena, ep)
+
+    def _ensure_arena(self):
+        """(arena, this model's plan).  Built lazily over this model alone unless a larger root was
+        attached with GradArena.attach(root) (bench / GraphedStep / GradientReducer do that so that
+        the task head's gradients live in the same flat buffer)."""
+        from .arena import GradArena
+        self._weight_table()
+        if self._arena is None or not self._arena[0]._still_valid():
+            self._arena = None
+            GradArena(self)                      # binds itself through _bind_arena
         return self._arena
 
     def grad_arena(self):
-        """The flat gradient buffer of the encoder layers (what gets all-reduced)."""
-        if self._arena is None:
-            self._build_arena()
-        return self._arena["flat"]
-
-    def _grad_table(self):
-        if self._arena is None:
-            self._build_arena()
-        A = self._arena
-        # accumulate iff the parameters still carry OUR arena views as .grad (i.e. zero_grad() was
-        # not called with set_to_none since the last backward)
-        p, v = A["views"][0]
-        accumulate = p.grad is not None and p.grad.data_ptr() == v.data_ptr()
-        A["small32"].zero_()
-        return A["gtable"], accumulate
+        """The flat gradient buffer this model's parameters live in (what gets all-reduced)."""
+        return self._ensure_arena()[0].flat
 
     def _finish_grads(self, accumulate, lo=0, hi=None):
-        """fp32 -> 16-bit for the small (bias / LayerNorm) gradients of layers [lo, hi) and, on a
-        fresh backward, attach the arena views as the parameters' .grad."""
+        """fp32 -> 16-bit for the small (bias / LayerNorm) gradients of layers [lo, hi)."""
         lib = _bind()
-        A = self._arena
+        arena, ep = self._arena
         NL = self.config.num_hidden_layers
         hi = NL if hi is None else hi
-        flat, small32, n = A["flat"], A["small32"], A["small_n"]
+        flat, small32, n = arena.flat, ep["small32"], ep["small_n"]
         dt = _lib.dtype_code(flat.dtype)
-        stream = _lib.current_stream()
-        dst0 = flat[lo * A["per_layer"] + A["big_n"]:]
+        dst0 = flat[ep["layer0"] + lo * ep["per_layer"] + ep["big_n"]:]
         _lib.check(lib.ub200_cvt_from_f32_strided(small32[lo * n:].data_ptr(), dst0.data_ptr(), n, hi - lo,
-                                                  n, A["per_layer"], 1 if accumulate else 0, dt, stream))
-        if not accumulate and lo == 0:
-            for p, v in A["views"]:
-                if p.requires_grad:
-                    if p.grad is None:
-                        p.grad = v
-                    elif p.grad.data_ptr() != v.data_ptr():   # a foreign gradient tensor: add into it
-                        p.grad.add_(v)
+                                                  n, ep["per_layer"], 1 if accumulate else 0, dt,
+                                                  _lib.current_stream()))
 
     def arena_slice(self, lo, hi):
         """Flat gradient slice of encoder layers [lo, hi) (contiguous)."""
-        if self._arena is None:
-            self._build_arena()
-        per = self._arena["per_layer"]
-        return self._arena["flat"][lo * per:hi * per]
+        arena, ep = self._ensure_arena()
+        return arena.flat[ep["layer0"] + lo * ep["per_layer"]:ep["layer0"] + hi * ep["per_layer"]]
 
     # ------------------------------------------------------------------ embeddings (reference API)
     def _compute_txt_embeddings(self, input_ids, position_ids, txt_type_ids=None):
@@ -860,14 +960,9 @@ class UniterModel(UniterPreTrainedModel):
             # unpack indices) is integer arithmetic done on the HOST and shipped in one small H2D
             # copy — no device reads, no index kernels
             lens_h = hit["lens_host"]
-            T = int(sum(lens_h))
-            host, (o_cu, o_pack, o_unpack) = _prefix_pack_host(lens_h, L)
+            host, offs, T = _prefix_pack_host(lens_h, L)
             devbuf = _META_RING.upload(host, dev)
-            cu = devbuf[o_cu:o_cu + B + 1]
-            pack_idx = devbuf[o_pack:o_pack + T]
-            unpack_idx = devbuf[o_unpack:o_unpack + B * L]
-            meta = dict(batch=B, L=L, total=T, max_seqlen=max(lens_h) if lens_h else 0,
-                        cu_seqlens=cu, pack_idx=pack_idx, unpack_idx=unpack_idx, lens_host=lens_h)
+            meta = _meta_from_buffer(devbuf, offs, B, L, T, max(lens_h) if lens_h else 0, lens_h, False)
             _meta_store(attention_mask, meta)
             return meta
         else:
@@ -882,10 +977,11 @@ class UniterModel(UniterPreTrainedModel):
             cu[1:] = torch.cumsum(lens, 0)
             # [T] -> b*L+j ; size is known from the host-side lengths, so no second sync
             pack_idx = torch.nonzero_static(am.reshape(-1), size=T).squeeze(1).to(torch.int32)
-        unpack_idx = torch.full((B * L,), -1, device=dev, dtype=torch.int32)
-        unpack_idx[pack_idx.long()] = torch.arange(T, device=dev, dtype=torch.int32)
+        unpack_ext = torch.full((B * L + 1,), -1, device=dev, dtype=torch.int32)
+        unpack_ext[pack_idx.long()] = torch.arange(T, device=dev, dtype=torch.int32)
         meta = dict(batch=B, L=L, total=T, max_seqlen=max(lens_h) if lens_h else 0,
-                    cu_seqlens=cu, pack_idx=pack_idx, unpack_idx=unpack_idx, lens_host=lens_h)
+                    cu_seqlens=cu, pack_idx=pack_idx, pack_inv=pack_idx, unpack_idx=unpack_ext[:B * L],
+                    unpack_ext=unpack_ext, lens_host=lens_h, n_batch=B)
         _meta_store(attention_mask, meta)
         return meta
 
@@ -903,7 +999,7 @@ class UniterModel(UniterPreTrainedModel):
         meta = self._pack_meta(attention_mask)
         if meta["total"] == 0:
             raise ValueError("attention_mask selects no tokens")
-        B, L = meta["batch"], meta["L"]
+        B, L = meta["n_batch"], meta["L"]
         # ---- embeddings (model/model.py:347-360) computed straight into PACKED rows by libub200
         if input_ids is None:
             mode = 2
@@ -922,18 +1018,13 @@ class UniterModel(UniterPreTrainedModel):
             raise NotImplementedError("text / image embedding dropout probabilities differ")
         if img_masks is not None:
             ie.mask_embedding.weight.data[0, :].fill_(0)          # model/model.py:263
+        if not hasattr(self, "_anchor") or self._anchor.device != attention_mask.device:
+            self._anchor = torch.zeros(1, device=attention_mask.device, requires_grad=True)
         x = _EmbedFront.apply(
-            self, meta, mode, input_ids, position_ids, img_feat, img_pos_feat, gather_index,
-            img_masks, txt_type_ids, img_type_ids, te.dropout.p if self.training else 0.0,
-            te.word_embeddings.weight, te.position_embeddings.weight, te.token_type_embeddings.weight,
-            te.LayerNorm.weight, te.LayerNorm.bias, ie.img_linear.weight, ie.img_linear.bias,
-            ie.img_layer_norm.weight, ie.img_layer_norm.bias, ie.pos_layer_norm.weight,
-            ie.pos_layer_norm.bias, ie.pos_linear.weight, ie.pos_linear.bias,
-            ie.mask_embedding.weight, ie.LayerNorm.weight, ie.LayerNorm.bias)       # [T, H] packed
+            self._anchor, self, meta, mode, input_ids, position_ids, img_feat, img_pos_feat, gather_index,
+            img_masks, txt_type_ids, img_type_ids, te.dropout.p if self.training else 0.0)  # [T, H] packed
 
         # ---- encoder stack on packed tokens
-        if not hasattr(self, "_anchor") or self._anchor.device != x.device:
-            self._anchor = torch.zeros(1, device=x.device, requires_grad=True)
         # (grad mode is always off inside Function.forward, so decide here whether the backward
         #  will need the per-layer activations)
         out = _EncoderStack.apply(x, self._anchor, self, meta, bool(output_all_encoded_layers),
@@ -946,13 +1037,13 @@ class UniterModel(UniterPreTrainedModel):
         out, meta = self.encode_packed(input_ids, position_ids, img_feat, img_pos_feat, attention_mask,
                                        gather_index, img_masks, output_all_encoded_layers,
                                        txt_type_ids, img_type_ids)
-        B, L = meta["batch"], meta["L"]
+        B, L = meta["n_batch"], meta["L"]
         H = self.config.hidden_size
         # ---- back to the reference's padded [B, L, H] view (zeros at masked positions)
         if output_all_encoded_layers:
             return [_GatherRows.apply(out[l], meta["unpack_idx"], meta["total"],
-                                      meta["pack_idx"]).view(B, L, H) for l in range(out.size(0))]
-        return _GatherRows.apply(out, meta["unpack_idx"], meta["total"], meta["pack_idx"]).view(B, L, H)
+                                      meta["pack_inv"]).view(B, L, H) for l in range(out.size(0))]
+        return _GatherRows.apply(out, meta["unpack_idx"], meta["total"], meta["pack_inv"]).view(B, L, H)
 
 
 def gather_packed_rows(packed, rows):

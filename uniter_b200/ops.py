@@ -15,7 +15,7 @@ from ._lib import (EPI_ACCUM, EPI_ATOMIC, EPI_BIAS, EPI_COLSUM, EPI_DGELU, EPI_D
 def gemm(a, b, *, a_major=0, b_major=0, bias=None, residual=None, aux=None, out=None,
          gelu=False, dgelu=False, accumulate=False, out_fp32=False, colsum=None,
          dropout_p=0.0, rng_seed=0, rng_stream=0, tile_n=0, max_ctas=0, cluster=0, k_splits=0,
-         n_valid=0, _debug_flags=0):
+         n_valid=0, rng_offset_dev=None, _debug_flags=0):
     """D = epilogue(A . B^T) on the tcgen05 GEMM core.  Returns `out` (and pre-activation if gelu).
 
     a: [M,K] (a_major=0) or [K,M] (a_major=1);  b: [N,K] (b_major=0) or [K,N] (b_major=1).
@@ -76,12 +76,13 @@ def gemm(a, b, *, a_major=0, b_major=0, bias=None, residual=None, aux=None, out=
         ldo=out.stride(0),
         dropout_p=float(dropout_p), rng_seed=int(rng_seed), rng_stream=int(rng_stream),
         tile_n=int(tile_n), max_ctas=int(max_ctas), cluster=int(cluster), k_splits=int(k_splits),
-        n_valid=int(n_valid))
+        n_valid=int(n_valid), rng_offset_dev=rng_offset_dev)
     _lib.check(lib.ub200_gemm(C.byref(args), _lib.current_stream()))
     return (out, out2) if gelu else out
 
 
-def attn_fwd(qkv, cu_seqlens, max_seqlen, num_heads, dropout_p=0.0, rng_seed=0, rng_stream=0):
+def attn_fwd(qkv, cu_seqlens, max_seqlen, num_heads, dropout_p=0.0, rng_seed=0, rng_stream=0,
+             rng_offset_dev=None):
     """ctx [T, H], lse [heads, T] = fused varlen attention over packed qkv [T, 3H]."""
     lib = _lib.load()
     T, H3 = qkv.shape
@@ -92,13 +93,13 @@ def attn_fwd(qkv, cu_seqlens, max_seqlen, num_heads, dropout_p=0.0, rng_seed=0, 
                       cu_seqlens=cu_seqlens.data_ptr(), batch=cu_seqlens.numel() - 1,
                       total_tokens=T, max_seqlen=max_seqlen, hidden=H, num_heads=num_heads,
                       dtype=_lib.dtype_code(qkv.dtype), dropout_p=float(dropout_p),
-                      rng_seed=int(rng_seed), rng_stream=int(rng_stream))
+                      rng_seed=int(rng_seed), rng_stream=int(rng_stream), rng_offset_dev=rng_offset_dev)
     _lib.check(lib.ub200_attn_fwd(C.byref(a), _lib.current_stream()))
     return ctx, lse
 
 
 def attn_bwd(qkv, ctx, lse, dctx, cu_seqlens, max_seqlen, num_heads, dropout_p=0.0, rng_seed=0,
-             rng_stream=0, dbias=None):
+             rng_stream=0, dbias=None, rng_offset_dev=None):
     lib = _lib.load()
     T, H3 = qkv.shape
     H = H3 // 3
@@ -111,7 +112,8 @@ def attn_bwd(qkv, ctx, lse, dctx, cu_seqlens, max_seqlen, num_heads, dropout_p=0
                       dtype=_lib.dtype_code(qkv.dtype), dropout_p=float(dropout_p),
                       rng_seed=int(rng_seed), rng_stream=int(rng_stream),
                       dctx=dctx.data_ptr(), dqkv=dqkv.data_ptr(),
-                      workspace=ws.data_ptr() if ws_bytes else None, dbias=_lib.ptr(dbias))
+                      workspace=ws.data_ptr() if ws_bytes else None, dbias=_lib.ptr(dbias),
+                      rng_offset_dev=rng_offset_dev)
     _lib.check(lib.ub200_attn_bwd(C.byref(a), _lib.current_stream()))
     return dqkv
 
@@ -127,7 +129,7 @@ def layernorm_fwd(x, gamma, beta):
 
 def layernorm_bwd(dy, x, gamma, dropout_p=0.0, rng_seed=0, rng_stream=0, want_dbias=True,
                   row_kind=None, kind=0, dropout_on_dy=False, dx=None, dgamma=None, dbeta=None, dbias=None,
-                  zero_inactive=False):
+                  zero_inactive=False, rng_offset_dev=None):
     """Returns dx, dx_drop (or None), dgamma, dbeta, dbias (fp32)."""
     lib = _lib.load()
     rows, H = x.shape
@@ -145,7 +147,8 @@ def layernorm_bwd(dy, x, gamma, dropout_p=0.0, rng_seed=0, rng_stream=0, want_db
                        dbias=_lib.ptr(dbias), rows=rows, hidden=H, dtype=_lib.dtype_code(x.dtype),
                        dropout_p=float(dropout_p), rng_seed=int(rng_seed), rng_stream=int(rng_stream),
                        row_kind=_lib.ptr(row_kind), kind=int(kind),
-                       dropout_on_dy=(1 if dropout_on_dy else 0) | (2 if zero_inactive else 0))
+                       dropout_on_dy=(1 if dropout_on_dy else 0) | (2 if zero_inactive else 0),
+                       rng_offset_dev=rng_offset_dev)
     _lib.check(lib.ub200_layernorm_bwd(C.byref(a), _lib.current_stream()))
     return dx, dx_drop, dgamma, dbeta, dbias
 

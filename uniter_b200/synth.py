@@ -131,3 +131,20 @@ def uniter_state_shapes(hidden, layers, inter, vocab, max_pos, type_vocab, img_d
         s[p + "output.LayerNorm.weight"] = (H,)
         s[p + "output.LayerNorm.bias"] = (H,)
     return s
+
+
+def pad_mlm_index(batch, multiple=64):
+    """Fixed-size masked-token lists for CUDA-graph replay: `mlm_index` is padded to a multiple of
+    `multiple` with B * L ("no row": UniterForMLM maps it to a zero row) and `mlm_targets` with -1
+    (ignored by the cross-entropy: loss 0, no gradient); `mlm_inv_n` = 1 / number of real masked
+    tokens, so that `loss.sum() * mlm_inv_n` is the reference's `loss.mean()`
+    (model/pretrain.py:122-127 + pretrain.py:297)."""
+    idx, tgt = batch["mlm_index"], batch["mlm_targets"]
+    n = idx.numel()
+    n_pad = max((n + multiple - 1) // multiple * multiple, multiple)
+    B, L = batch["attn_masks"].shape
+    out = dict(batch)
+    out["mlm_index"] = torch.cat([idx, torch.full((n_pad - n,), B * L, dtype=idx.dtype)])
+    out["mlm_targets"] = torch.cat([tgt, torch.full((n_pad - n,), -1, dtype=tgt.dtype)])
+    out["mlm_inv_n"] = torch.tensor([1.0 / max(n, 1)], dtype=torch.float32)
+    return out
