@@ -76,6 +76,7 @@ int ub200_profile_collect(float* ms_per_tag, int* launches_per_tag, int ntags);
  *   UB200_EPI_DROPOUT   v = keep(m,n) ? v / (1-p) : 0          (Philox, regenerated in bwd)
  *   UB200_EPI_RESIDUAL  v += residual[m,n]
  *   UB200_EPI_GELU      out2[m,n] = v ; v = gelu_erf(v)         (model/layer.py:31-37)
+ *   UB200_EPI_TANH      v = tanh(v)                              (BertPooler, model/layer.py:184)
  *   UB200_EPI_DGELU     v *= gelu_erf'(aux[m,n])
  *   UB200_EPI_ACCUM     v += out[m,n]   (previous contents, e.g. gradient accumulation)
  *   UB200_EPI_OUT_F32   out is fp32 instead of the 16-bit dtype
@@ -93,6 +94,7 @@ enum {
   UB200_EPI_OUT_F32 = 64,
   UB200_EPI_COLSUM = 128,
   UB200_EPI_ATOMIC = 256,
+  UB200_EPI_TANH = 512,
 };
 
 typedef struct {
@@ -364,6 +366,8 @@ int ub200_embed_bwd_colsums(const ub200_embed_colsum_args* args, ub200_stream_t 
  *   ub200_ce_bwd   dlogits[r, c] = (softmax - onehot) * dloss[r] for c < vocab, 0 for
  *                  vocab <= c < ncols; dlogits may alias logits
  *   ub200_dgelu_mul  out = dy * gelu_erf'(pre)   (n elements, n % 8 == 0)
+ *   ub200_dtanh_mul  out = dy * (1 - y^2), y = tanh(pre) as saved by the forward: backward of
+ *                    BertPooler (model/layer.py:179-185), whose forward is ub200_gemm with UB200_EPI_TANH
  * ------------------------------------------------------------------------------------------ */
 int ub200_ce_fwd(const void* logits, int64_t ld, const int64_t* targets, float* loss, float* lse,
                  int32_t rows, int32_t vocab, int32_t dtype, ub200_stream_t stream);
@@ -371,6 +375,8 @@ int ub200_ce_bwd(const void* logits, void* dlogits, int64_t ld, const int64_t* t
                  const float* lse, const float* dloss, int32_t rows, int32_t vocab, int32_t ncols,
                  int32_t dtype, ub200_stream_t stream);
 int ub200_dgelu_mul(const void* dy, const void* pre, void* out, int64_t n, int32_t dtype,
+                    ub200_stream_t stream);
+int ub200_dtanh_mul(const void* dy, const void* y, void* out, int64_t n, int32_t dtype,
                     ub200_stream_t stream);
 
 /* Multi-tensor AdamW on fp32 master weights: replaces optim/adamw.py:43-103 (+ the apex O2
@@ -394,14 +400,36 @@ typedef struct {
   float lr_wd;
   int32_t grad_dtype;     /* UB200_F16 / UB200_BF16 / UB200_F32 */
   int32_t model_dtype;
+  /* device-state mode (ub200_adam_state given to ub200_adamw_step): */
+  float weight_decay;     /* lr_wd = lr * weight_decay with lr = lr_dev[group] */
+  int32_t group;          /* index into lr_dev */
+  int32_t step_offset;    /* this tensor's step count = state->step - step_offset (a parameter that got
+                             its first gradient later than the others) */
+  int32_t flags;          /* bit 0: bias-corrected step size (optim/adamw.py:82-86) */
 } ub200_adam_segment;
+
+/* Device-resident optimizer state: lets a whole training step (loss scaling included) run without
+ * the host ever reading a gradient — apex amp's dynamic loss scaler (train_vqa.py:152,190-192) skips
+ * the step when a gradient overflowed; here ub200_adam_prep decides that ON THE DEVICE from the sum of
+ * squares: found_inf = !isfinite(sumsq); a finite step increments `step`, an overflowed one increments
+ * `skipped` and ub200_adamw_step leaves masters, moments and model weights untouched. */
+typedef struct {
+  int32_t step;       /* number of optimizer steps actually applied */
+  int32_t found_inf;  /* 1 iff the last ub200_adam_prep saw a non-finite gradient norm */
+  int32_t skipped;    /* number of skipped (overflowed) steps */
+  int32_t _pad;
+} ub200_adam_state;
+int ub200_adam_prep(const float* sumsq, ub200_adam_state* state_dev, ub200_stream_t stream);
 enum { UB200_F32 = 2 };
 int32_t ub200_adam_chunk(void);
 int ub200_grad_sumsq(const ub200_adam_segment* segs_dev, const int32_t* blk_start_dev, int32_t nseg,
                      int32_t nblocks, float* out, ub200_stream_t stream);
+/* state_dev / lr_dev NULL: legacy mode (host-computed step_size / lr_wd per segment, no skipping).
+ * Otherwise: skip when state->found_inf; lr = lr_dev[seg.group]; bias correction from state->step. */
 int ub200_adamw_step(const ub200_adam_segment* segs_dev, const int32_t* blk_start_dev, int32_t nseg,
                      int32_t nblocks, float beta1, float beta2, float eps, float inv_scale,
-                     float max_norm, const float* sumsq, ub200_stream_t stream);
+                     float max_norm, const float* sumsq, const ub200_adam_state* state_dev,
+                     const float* lr_dev, ub200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -64,7 +64,7 @@ def test_fused_adamw_master_weights_16bit_model(dtype):
     opt2 = FusedAdamW([{"params": [params[0], params[2]], "weight_decay": 0.01},
                        {"params": [params[1], params[3]], "weight_decay": 0.0}], lr=1e-3)
     opt2.load_state_dict(sd)
-    assert opt2.state[id(params[2])]["step"] == 3
+    assert opt2.state_dict()["state"][1]["step"] == 3          # params[2] = second tensor of group 0
     assert torch.equal(opt2.state[id(params[2])]["exp_avg"], opt.state[id(params[2])]["exp_avg"])
 
 
@@ -91,3 +91,40 @@ def test_fused_adamw_steps_the_model_from_its_gradient_arena():
         losses.append(loss.item())
     assert all(l == l for l in losses)
     assert losses[-1] < losses[0] - 0.1, losses
+
+
+def test_fused_adamw_skips_overflowed_steps_on_the_device():
+    """fp16 + loss scaling: an inf / NaN gradient must not poison masters or moments (g * 0 = NaN);
+    like apex's dynamic scaler the step is skipped — decided on the device, no host sync — the step
+    count does not advance (bias correction of the next real step is that of step 1) and
+    `found_inf` is raised for the caller to lower its loss scale."""
+    from uniter_b200.optim import FusedAdamW
+    gen = torch.Generator().manual_seed(5)
+    shapes = [(130, 8), (33,)]
+    p0 = [(torch.randn(s, generator=gen) * 0.05).half() for s in shapes]
+    params = [torch.nn.Parameter(x.clone().cuda()) for x in p0]
+    grads = [torch.nn.Parameter(torch.zeros_like(p)) for p in params]      # static gradient buffers
+    for p, g in zip(params, grads):
+        p.grad = g.data
+    opt = FusedAdamW(params, lr=1e-3, weight_decay=0.01)
+    for bad in (float("inf"), float("nan")):
+        for p in params:
+            p.grad.copy_((torch.randn(p.shape, generator=gen) * 0.01).half())
+        params[0].grad[3, 2] = bad
+        opt.step(grad_scale=64.0, max_grad_norm=1.0)
+        assert int(opt.found_inf.item()) == 1
+        for p, x in zip(params, p0):
+            assert torch.equal(p.detach().cpu(), x)
+            st = opt.state[id(p)]
+            assert torch.equal(st["master"].cpu(), x.float())
+            assert (st["exp_avg"] == 0).all() and (st["exp_avg_sq"] == 0).all()
+    assert opt.skipped_steps() == 2 and opt._applied_steps() == 0
+    gs = [(torch.randn(p.shape, generator=gen) * 0.01 * 64.0).half() for p in params]
+    for p, g in zip(params, gs):
+        p.grad.copy_(g)
+    opt.step(grad_scale=64.0, max_grad_norm=-1.0)
+    assert int(opt.found_inf.item()) == 0 and opt._applied_steps() == 1
+    for i, (p, x) in enumerate(zip(params, p0)):
+        want, _, _ = orc.adamw_step(x.float(), gs[i].float() / 64.0, torch.zeros(x.shape), torch.zeros(x.shape),
+                                    1, 1e-3, weight_decay=0.01)
+        np.testing.assert_allclose(opt.state[id(p)]["master"].cpu().numpy(), want.numpy(), atol=1e-6, rtol=1e-5)

@@ -202,3 +202,70 @@ def test_unmodified_reference_hard_negative_itm_over_drop_in_encoder():
             assert (loss.float().cpu() - rloss.detach()).abs().max().item() <= 1e-2, sf
             compared += 1
     assert compared >= 1
+
+
+@pytest.mark.parametrize("use_index", [True, False])
+def test_library_pretraining_heads_match_the_reference_model(use_index):
+    """OUR UniterForPretraining (every head on libub200: LibTransform / LibLinear / fused MLM head /
+    library pooler) against the UNMODIFIED reference UniterForPretraining over the reference encoder
+    on CPU fp32 (weights rounded to fp16): logits of mlm / mrfr / mrc / itm within 1e-2 (north
+    star), per-element losses, and gradients of a multi-task loss for the head parameters and both
+    tied weights (decoder <-> word embeddings, feat_regress.weight <-> img_linear.weight)."""
+    from uniter_b200.heads import UniterForPretraining
+    from uniter_b200.synth import seeded_state, synth_batch, synth_mrm
+    rm, rpre = ref_loader.load("model.model", "model.pretrain")
+    cfg = _tiny_ref_config(rm)
+    ref = rpre.UniterForPretraining(cfg, 64, 11)
+    st = seeded_state({k: tuple(v.shape) for k, v in ref.state_dict().items()}, seed=4)
+    ref.load_state_dict({k: v.half().float() for k, v in st.items()}, strict=True)
+    ref.eval()
+    mod = UniterForPretraining(util.tiny_config(), 64, 11)
+    missing = mod.load_state_dict(st, strict=True)
+    mod = mod.cuda().half().eval()
+    base = synth_batch(5, 5, 9, 4, 8, seed=17, img_dim=64, vocab_size=2000, mlm_prob=0.3)
+    mb = synth_mrm(base, mask_prob=0.3, label_dim=11, seed=3)
+    keys = [k for k, v in mb.items() if torch.is_tensor(v)]
+    if not use_index:           # the reference's own boolean-mask row selection
+        keys = [k for k in keys if k not in ("mlm_index", "mlm_targets", "mrm_index", "mrm_valid", "mrm_inv_n")]
+    cb = {k: (mb[k].half().float() if mb[k].is_floating_point() else mb[k]) for k in keys}
+    db = {k: mb[k].cuda() for k in keys}
+    cb["targets"] = torch.tensor([1, 0, 1, 1, 0])
+    db["targets"] = cb["targets"].cuda()
+    cb["ot_inputs"] = None
+    plain_c = dict(cb, img_feat=base["img_feat"].half().float())      # mlm / itm see unmasked regions
+    plain_d = dict(db, img_feat=base["img_feat"].cuda())
+    total_c, total_d = 0.0, 0.0
+    for task in ("mlm", "mrfr", "mrc", "mrc-kl", "itm"):
+        bc, bd = (plain_c, plain_d) if task in ("mlm", "itm") else (cb, db)
+        with torch.no_grad():
+            want = ref(bc, task=task, compute_loss=False)
+            got = mod(bd, task=task, compute_loss=False)
+        want = want[0] if isinstance(want, tuple) else want
+        got = got[0] if isinstance(got, tuple) else got
+        assert got.shape == want.shape, (task, got.shape, want.shape)
+        err = (got.float().cpu() - want).abs().max().item()
+        assert err <= 1e-2, (task, err)
+        lw = ref(bc, task=task, compute_loss=True)
+        lg = mod(bd, task=task, compute_loss=True)
+        lw = lw[0] if isinstance(lw, tuple) else lw
+        lg = lg[0] if isinstance(lg, tuple) else lg
+        assert lg.shape == lw.shape, (task, lg.shape, lw.shape)
+        assert (lg.float().cpu() - lw.detach()).abs().max().item() <= 3e-2, task
+        total_c = total_c + lw.float().mean()
+        total_d = total_d + lg.float().mean()
+    (total_d * 64.0).backward()
+    total_c.backward()
+    gp = dict(mod.named_parameters())
+    rp = dict(ref.named_parameters())
+    for name in ("feat_regress.net.0.weight", "feat_regress.net.2.weight", "feat_regress.bias",
+                 "region_classifier.net.0.weight", "region_classifier.net.3.weight",
+                 "region_classifier.net.3.bias", "itm_output.weight", "itm_output.bias",
+                 "uniter.pooler.dense.weight", "uniter.pooler.dense.bias",
+                 "cls.predictions.transform.dense.weight", "cls.predictions.bias",
+                 "uniter.embeddings.word_embeddings.weight", "uniter.img_embeddings.img_linear.weight",
+                 "uniter.img_embeddings.mask_embedding.weight",
+                 "uniter.encoder.layer.1.output.dense.weight"):
+        got = gp[name].grad.float().cpu() / 64.0
+        want = rp[name].grad
+        rel = ((got - want).norm() / (want.norm() + 1e-12)).item()
+        assert rel <= 4e-2, (name, rel)

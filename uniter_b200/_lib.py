@@ -13,6 +13,7 @@ F16, BF16 = 0, 1
 EPI_BIAS, EPI_DROPOUT, EPI_RESIDUAL, EPI_GELU = 1, 2, 4, 8
 EPI_DGELU, EPI_ACCUM, EPI_OUT_F32, EPI_COLSUM = 16, 32, 64, 128
 EPI_ATOMIC = 256
+EPI_TANH = 512
 
 
 class GemmArgs(C.Structure):
@@ -88,7 +89,9 @@ class AdamSegment(C.Structure):
     _fields_ = [("grad", C.c_void_p), ("master", C.c_void_p), ("exp_avg", C.c_void_p),
                 ("exp_avg_sq", C.c_void_p), ("model", C.c_void_p), ("n", C.c_int64),
                 ("step_size", C.c_float), ("lr_wd", C.c_float),
-                ("grad_dtype", C.c_int32), ("model_dtype", C.c_int32)]
+                ("grad_dtype", C.c_int32), ("model_dtype", C.c_int32),
+                ("weight_decay", C.c_float), ("group", C.c_int32), ("step_offset", C.c_int32),
+                ("flags", C.c_int32)]
 
 
 F32 = 2
@@ -150,6 +153,8 @@ def load():
                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.ub200_dgelu_mul.restype = C.c_int
     lib.ub200_dgelu_mul.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    lib.ub200_dtanh_mul.restype = C.c_int
+    lib.ub200_dtanh_mul.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     lib.ub200_cvt_from_f32.restype = C.c_int
     lib.ub200_cvt_from_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     lib.ub200_adam_chunk.restype = C.c_int32
@@ -157,7 +162,10 @@ def load():
     lib.ub200_grad_sumsq.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.ub200_adamw_step.restype = C.c_int
     lib.ub200_adamw_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float,
-                                     C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+                                     C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]
+    lib.ub200_adam_prep.restype = C.c_int
+    lib.ub200_adam_prep.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ub200_gather_rows.restype = C.c_int
     lib.ub200_gather_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     _lib = lib

@@ -93,6 +93,21 @@ __device__ __forceinline__ void store8(void* base, long long idx, const float (&
 }
 
 
+// Bring-up instrumentation, compiled only with -DUB200_BRINGUP (never in the shipped library):
+// epilogue bit 27 turns p.colsum into a per-CTA timeline buffer (clock64 stamps), bit 30 drops a
+// tile's epilogue, bit 29 drops its stores.
+#ifdef UB200_BRINGUP
+#define UB_TRACE(slot)                                                                      \
+  do {                                                                                      \
+    if (p.epilogue & (1 << 27))                                                             \
+      reinterpret_cast<long long*>(p.colsum)[blockIdx.x * 16 + (slot)] = clock64();         \
+  } while (0)
+#define UB_BRINGUP_HAS(E, bit) (E).has(bit)
+#else
+#define UB_TRACE(slot) do { } while (0)
+#define UB_BRINGUP_HAS(E, bit) false
+#endif
+
 // --------------------------------------------------------------------------------- epilogue
 // One epilogue warp: rows = TMEM lanes [32*quarter, +32) of the CTA's 128-row accumulator (this
 // thread owns global row `row`), columns = half `chalf` of the BN columns, in 32-column blocks.
@@ -173,7 +188,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmParams& p, uint32_t t_ac
       }
     }
     if (col0 >= p.N) continue;        // warp-uniform
-    if (E.has(1 << 30)) continue;     // bring-up / profiling only: drop the tile
+    if (UB_BRINGUP_HAS(E, 1 << 30)) continue;   // bring-up only: drop the tile
 
     __syncwarp();                     // previous block's readers are done with `stage`
 #pragma unroll
@@ -216,6 +231,10 @@ __device__ __forceinline__ void epilogue_warp(const GemmParams& p, uint32_t t_ac
         }
         store8<kBF16>(p.out2, static_cast<long long>(row) * p.ldo + col, pre);
       }
+      if (E.has(UB200_EPI_TANH)) {       // generic (runtime-mask) kernel only
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = tanhf(v[i]);
+      }
       if (E.has(UB200_EPI_DGELU)) {
         float t[8];
         if (E.has(UB200_EPI_RESIDUAL))   // generic path only: aux was not prefetched
@@ -250,7 +269,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmParams& p, uint32_t t_ac
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] += t[i];
         }
-        if (!E.has(1 << 29)) store8<kBF16>(p.out, static_cast<long long>(row) * p.ldo + col, v);
+        if (!UB_BRINGUP_HAS(E, 1 << 29)) store8<kBF16>(p.out, static_cast<long long>(row) * p.ldo + col, v);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) csum[i] += v[i];
@@ -273,12 +292,7 @@ __device__ __forceinline__ void epilogue_warp(const GemmParams& p, uint32_t t_ac
   }
 }
 
-// bring-up only: epilogue bit 27 turns p.colsum into a per-CTA timeline buffer (clock64 stamps)
-#define UB_TRACE(slot)                                                                      \
-  do {                                                                                      \
-    if (p.epilogue & (1 << 27))                                                             \
-      reinterpret_cast<long long*>(p.colsum)[blockIdx.x * 16 + (slot)] = clock64();         \
-  } while (0)
+
 
 __device__ __forceinline__ DropoutRng make_rng(const GemmParams& p) {
   DropoutRng rng;

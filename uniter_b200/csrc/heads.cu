@@ -134,7 +134,8 @@ ce_bwd_kernel(const void* logits_, void* out_, long long ld, const long long* __
 }
 
 // ------------------------------------------------------------------------------ dy * gelu'(pre)
-template <bool kBF16>
+// kTanh: out = dy * (1 - y^2) with y = tanh(pre) saved by the forward (BertPooler backward)
+template <bool kBF16, bool kTanh = false>
 __global__ void __launch_bounds__(256)
 dgelu_mul_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ pre, uint4* __restrict__ out,
                  long long nvec) {
@@ -146,7 +147,7 @@ dgelu_mul_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ pre, ui
     h_unpack8<kBF16>(__ldg(dy + i), a);
     h_unpack8<kBF16>(__ldg(pre + i), b);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) a[e] *= dgelu_erf(b[e]);
+    for (int e = 0; e < 8; ++e) a[e] *= kTanh ? (1.0f - b[e] * b[e]) : dgelu_erf(b[e]);
     out[i] = h_pack8<kBF16>(a);
   }
 }
@@ -212,7 +213,19 @@ struct AdamHyper {
   float inv_scale;        // 1 / loss_scale (gradient unscaling)
   float max_norm;         // <= 0: no clipping
   const float* sumsq;     // device scalar from sumsq_kernel (of the SCALED gradients) or NULL
+  const ub200_adam_state* state;   // device-resident step counter / overflow flag, or NULL (legacy)
+  const float* lr;                 // per-group learning rates (device), with `state`
 };
+
+// found_inf / step bookkeeping on the device (one thread), between sumsq_kernel and adamw_kernel
+__global__ void adam_prep_kernel(const float* __restrict__ sumsq, ub200_adam_state* __restrict__ st) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const float s = *sumsq;
+  const bool finite = (s == s) && (fabsf(s) <= 3.0e38f);
+  st->found_inf = finite ? 0 : 1;
+  if (finite) st->step += 1; else st->skipped += 1;
+}
 
 __global__ void __launch_bounds__(256)
 adamw_kernel(const ub200_adam_segment* __restrict__ segs, const int* __restrict__ blk_start, int nseg,
@@ -222,6 +235,21 @@ adamw_kernel(const ub200_adam_segment* __restrict__ segs, const int* __restrict_
   const int s = find_segment(blk_start, nseg, blockIdx.x);
   const ub200_adam_segment sg = segs[s];
   const long long base = static_cast<long long>(blockIdx.x - blk_start[s]) * ADAM_CHUNK;
+  float step_size = sg.step_size, lr_wd = sg.lr_wd;
+  if (h.state != nullptr) {
+    // an overflowed gradient (fp16 loss scaling) must not touch masters / moments / weights:
+    // g * 0 would be NaN for g = inf (apex's dynamic scaler skips such a step)
+    if (h.state->found_inf) return;
+    const float lr = __ldg(h.lr + sg.group);
+    step_size = lr;
+    if (sg.flags & 1) {
+      // once per CTA, in double: 1 - beta^t loses all its digits in fp32 for beta = 0.999, t = 1
+      const double t = static_cast<double>(h.state->step - sg.step_offset);
+      step_size = static_cast<float>(static_cast<double>(lr) * sqrt(1.0 - pow(static_cast<double>(h.beta2), t)) /
+                                     (1.0 - pow(static_cast<double>(h.beta1), t)));
+    }
+    lr_wd = lr * sg.weight_decay;
+  }
   float gmul = h.inv_scale;
   if (h.max_norm > 0.f && h.sumsq != nullptr) {
     // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), applied iff < 1
@@ -234,8 +262,8 @@ adamw_kernel(const ub200_adam_segment* __restrict__ segs, const int* __restrict_
     m = m * h.beta1 + (1.0f - h.beta1) * g;              // optim/adamw.py:77
     v = v * h.beta2 + (1.0f - h.beta2) * g * g;          // :78
     const float denom = sqrtf(v) + h.eps;                // :79
-    p = p - sg.step_size * (m / denom);                  // :81-88 (step_size bias-corrected on host)
-    if (sg.lr_wd > 0.f) p = p - sg.lr_wd * p;            // :99-100 decoupled decay AFTER the update
+    p = p - step_size * (m / denom);                     // :81-88 (bias-corrected step size)
+    if (lr_wd > 0.f) p = p - lr_wd * p;                  // :99-100 decoupled decay AFTER the update
   };
   // vector path: 4 elements per thread (16-byte fp32 accesses, 8-byte 16-bit accesses) when the
   // segment is a 16-bit parameter with a 16-bit gradient of the same type and everything is aligned
@@ -349,6 +377,28 @@ extern "C" int ub200_dgelu_mul(const void* dy, const void* pre, void* out, int64
   return 0;
 }
 
+extern "C" int ub200_dtanh_mul(const void* dy, const void* y, void* out, int64_t n, int32_t dtype,
+                               ub200_stream_t stream_) {
+  using namespace ub;
+  UB_CHECK_ARG(dy && y && out, "dtanh_mul: null pointer");
+  UB_CHECK_ARG(n > 0 && n % 8 == 0, "dtanh_mul: n must be a positive multiple of 8");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const long long nvec = n / 8;
+  long long blocks = (nvec + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  ProfScope ps(stream);
+  if (dtype == UB200_BF16)
+    UB_CHECK_CUDA(launch_pdl(dgelu_mul_kernel<true, true>, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, 1,
+                             reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(y),
+                             reinterpret_cast<uint4*>(out), nvec));
+  else
+    UB_CHECK_CUDA(launch_pdl(dgelu_mul_kernel<false, true>, dim3(static_cast<int>(blocks)), dim3(256), 0, stream, 1,
+                             reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(y),
+                             reinterpret_cast<uint4*>(out), nvec));
+  return 0;
+}
+
 extern "C" int32_t ub200_adam_chunk(void) { return ub::ADAM_CHUNK; }
 
 extern "C" int ub200_grad_sumsq(const ub200_adam_segment* segs_dev, const int32_t* blk_start_dev,
@@ -362,17 +412,28 @@ extern "C" int ub200_grad_sumsq(const ub200_adam_segment* segs_dev, const int32_
   return 0;
 }
 
+extern "C" int ub200_adam_prep(const float* sumsq, ub200_adam_state* state_dev, ub200_stream_t stream_) {
+  using namespace ub;
+  UB_CHECK_ARG(sumsq && state_dev, "adam_prep: null pointer");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ProfScope ps(stream);
+  UB_CHECK_CUDA(launch_pdl(adam_prep_kernel, dim3(1), dim3(1), 0, stream, 1, sumsq, state_dev));
+  return 0;
+}
+
 extern "C" int ub200_adamw_step(const ub200_adam_segment* segs_dev, const int32_t* blk_start_dev,
                                 int32_t nseg, int32_t nblocks, float beta1, float beta2, float eps,
                                 float inv_scale, float max_norm, const float* sumsq,
+                                const ub200_adam_state* state_dev, const float* lr_dev,
                                 ub200_stream_t stream_) {
   using namespace ub;
   UB_CHECK_ARG(segs_dev && blk_start_dev && nseg > 0 && nblocks > 0, "adamw_step: bad argument");
+  UB_CHECK_ARG((state_dev == nullptr) == (lr_dev == nullptr), "adamw_step: state_dev and lr_dev go together");
   UB_CHECK_ARG(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f,
                "adamw_step: invalid hyper-parameters");
   UB_CHECK_ARG(max_norm <= 0.f || sumsq, "adamw_step: clipping needs the sumsq scalar");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  AdamHyper h{beta1, beta2, eps, inv_scale, max_norm, sumsq};
+  AdamHyper h{beta1, beta2, eps, inv_scale, max_norm, sumsq, state_dev, lr_dev};
   ProfScope ps(stream);
   UB_CHECK_CUDA(launch_pdl(adamw_kernel, dim3(nblocks), dim3(256), 0, stream, 1, segs_dev, blk_start_dev,
                            nseg, h));

@@ -21,7 +21,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from . import ops
-from .model import UniterModel, UniterPreTrainedModel, gather_packed_rows
+from .model import LibLinear, UniterModel, UniterPreTrainedModel, gather_packed_rows
 
 
 class GELU(nn.Module):
@@ -171,6 +171,171 @@ class UniterForMLM(UniterPreTrainedModel):
         rows = meta["unpack_ext"][flat]                                # packed row of each masked token
         masked_output = gather_packed_rows(packed, rows)               # [n, H]
         return _MlmHead.apply(masked_output, self, targets, not compute_loss)
+
+
+class LibTransform(torch.autograd.Function):
+    """z = LayerNorm(gelu(h W^T + b)) — BertPredictionHeadTransform (model/layer.py:188-203) and the
+    `net.0 / net.1 / net.2` prefix of RegionFeatureRegression / RegionClassification
+    (model/pretrain.py:19-47) — on libub200: GEMM with the bias + GELU epilogue, LayerNorm kernels,
+    dGELU kernel, dgrad / wgrad GEMMs.  Gradients of parameters that live in a gradient arena are
+    written there directly."""
+
+    @staticmethod
+    def forward(ctx, h, dense_w, dense_b, ln_g, ln_b):
+        h = h.contiguous()
+        t, pre = ops.gemm(h, dense_w, bias=dense_b, gelu=True)
+        z = ops.layernorm_fwd(t, ln_g, ln_b)
+        ctx.save_for_backward(h, pre, t)
+        ctx.params = (dense_w, dense_b, ln_g, ln_b)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        h, pre, t = ctx.saved_tensors
+        dense_w, dense_b, ln_g, ln_b = ctx.params
+        dtype = h.dtype
+        dt, _, dg, db, _ = ops.layernorm_bwd(dz.contiguous(), t, ln_g, want_dbias=False)
+        dpre = ops.dgelu_mul(dt, pre)
+        dh = ops.gemm(dpre, dense_w, b_major=1) if ctx.needs_input_grad[0] else None
+        arena = getattr(dense_w, "_ub_arena", None)
+        if arena is not None and arena._still_valid() and all(id(q) in arena._views for q in ctx.params):
+            arena.mark_managed(ctx.params)
+            acc = arena.claim(list(ctx.params))
+            ops.gemm(dpre, h, a_major=1, b_major=1, out=arena.view(dense_w), accumulate=acc)
+            ops.cvt_from_f32(ops.colsum(dpre), dtype, out=arena.view(dense_b), accumulate=acc)
+            ops.cvt_from_f32(dg, dtype, out=arena.view(ln_g), accumulate=acc)
+            ops.cvt_from_f32(db, dtype, out=arena.view(ln_b), accumulate=acc)
+            return dh, None, None, None, None
+        return (dh, ops.gemm(dpre, h, a_major=1, b_major=1), ops.cvt_from_f32(ops.colsum(dpre), dtype),
+                ops.cvt_from_f32(dg, dtype), ops.cvt_from_f32(db, dtype))
+
+
+class RegionFeatureRegression(nn.Module):
+    """model/pretrain.py:19-32 (MRFR head): LN(gelu(dense(h))) @ img_linear.weight + bias — the
+    output projection is TIED to the image embedding's input projection, read as a [K, N] operand."""
+
+    def __init__(self, hidden_size, feat_dim, img_linear_weight):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(hidden_size, hidden_size), GELU(),
+                                 nn.LayerNorm(hidden_size, eps=1e-12))
+        self.weight = img_linear_weight
+        self.bias = nn.Parameter(torch.zeros(feat_dim))
+
+    def forward(self, input_):
+        hidden = LibTransform.apply(input_, self.net[0].weight, self.net[0].bias, self.net[2].weight,
+                                    self.net[2].bias)
+        return LibLinear.apply(hidden, self.weight, self.bias, True, False)
+
+
+class RegionClassification(nn.Module):
+    """model/pretrain.py:35-47 (MRC / MRC-kl head)."""
+
+    def __init__(self, hidden_size, label_dim):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(hidden_size, hidden_size), GELU(),
+                                 nn.LayerNorm(hidden_size, eps=1e-12), nn.Linear(hidden_size, label_dim))
+
+    def forward(self, input_):
+        hidden = LibTransform.apply(input_, self.net[0].weight, self.net[0].bias, self.net[2].weight,
+                                    self.net[2].bias)
+        return LibLinear.apply(hidden, self.net[3].weight, self.net[3].bias, False, False)
+
+
+def _masked_rows(packed, meta, mask2d, index):
+    """Rows of the packed encoder output selected by a [B, L] boolean mask (model/pretrain.py:129-133,
+    `_compute_masked_hidden`) — or by a loader-provided flat index list (b * L + j; entries equal to
+    B * L are padding of a fixed-size list -> zero rows), which needs no device read."""
+    if index is None:
+        pos = mask2d.nonzero(as_tuple=False)                   # device sync, like the reference
+        index = pos[:, 0] * meta["L"] + pos[:, 1]
+    return gather_packed_rows(packed, meta["unpack_ext"][index])
+
+
+class UniterForPretraining(UniterPreTrainedModel):
+    """model/pretrain.py:50-229 with every head on libub200: MLM (fused head + cross-entropy), MRFR,
+    MRC / MRC-kl (LibTransform + LibLinear over the masked REGION rows gathered straight from the
+    packed encoder output) and ITM (library pooler + LibLinear).  Same parameter names, weight tying
+    (cls.predictions.decoder <-> word_embeddings, feat_regress.weight <-> img_linear.weight) and
+    forward(batch, task, compute_loss) contract; the OT term of ITM (model/ot.py) is outside the hot
+    path and not implemented (ot_inputs must be None).
+
+    Fixed-shape (CUDA-graph friendly) variants of the reference's data-dependent row selections are
+    taken from the batch when the loader provides them: `mlm_index` / `mlm_targets`, `mrm_index`."""
+
+    def __init__(self, config, img_dim, img_label_dim):
+        super().__init__(config)
+        self.uniter = UniterModel(config, img_dim)
+        self.cls = BertOnlyMLMHead(config, self.uniter.embeddings.word_embeddings.weight)
+        self.feat_regress = RegionFeatureRegression(config.hidden_size, img_dim,
+                                                    self.uniter.img_embeddings.img_linear.weight)
+        self.region_classifier = RegionClassification(config.hidden_size, img_label_dim)
+        self.itm_output = nn.Linear(config.hidden_size, 2)
+        self.apply(self.init_weights)
+
+    def _encode(self, batch, img_masks=None):
+        return self.uniter.encode_packed(
+            batch["input_ids"], batch["position_ids"], batch["img_feat"], batch["img_pos_feat"],
+            batch["attn_masks"], batch["gather_index"], output_all_encoded_layers=False,
+            img_masks=img_masks, txt_type_ids=batch["txt_type_ids"])
+
+    def forward(self, batch, task, compute_loss=True):
+        batch = defaultdict(lambda: None, batch)
+        if task == "mlm":
+            return self.forward_mlm(batch, compute_loss)
+        if task == "mrfr":
+            return self.forward_mrfr(batch, compute_loss)
+        if task == "itm":
+            return self.forward_itm(batch, compute_loss)
+        if task.startswith("mrc"):
+            return self.forward_mrc(batch, task, compute_loss)
+        raise ValueError("invalid task")
+
+    def forward_mlm(self, batch, compute_loss=True):                      # model/pretrain.py:107-127
+        packed, meta = self._encode(batch)
+        L = meta["L"]
+        if batch["mlm_index"] is not None:
+            flat, targets = batch["mlm_index"], batch["mlm_targets"]
+        else:
+            txt_labels = batch["txt_labels"]
+            pos = (txt_labels != -1).nonzero(as_tuple=False)
+            flat = pos[:, 0] * L + pos[:, 1]
+            targets = txt_labels[pos[:, 0], pos[:, 1]]
+        masked_output = gather_packed_rows(packed, meta["unpack_ext"][flat])
+        return _MlmHead.apply(masked_output, self, targets, not compute_loss)
+
+    def forward_mrfr(self, batch, compute_loss=True):                     # model/pretrain.py:135-154
+        packed, meta = self._encode(batch, img_masks=batch["img_masks"])
+        masked_output = _masked_rows(packed, meta, batch["img_mask_tgt"], batch["mrm_index"])
+        prediction_feat = self.feat_regress(masked_output)
+        if compute_loss:
+            return F.mse_loss(prediction_feat, batch["feat_targets"].to(prediction_feat.dtype),
+                              reduction="none")
+        return prediction_feat
+
+    def forward_itm(self, batch, compute_loss=True):                      # model/pretrain.py:156-199
+        if batch["ot_inputs"] is not None:
+            raise NotImplementedError("the OT / WRA term (model/ot.py) is outside the hot path")
+        packed, meta = self._encode(batch)
+        B, L = meta["n_batch"], meta["L"]
+        cls_rows = meta["unpack_ext"][::L][:B]          # packed row of position (b, 0): the [CLS] token
+        pooled = self.uniter.pooler(gather_packed_rows(packed, cls_rows.contiguous()))
+        itm_scores = LibLinear.apply(pooled, self.itm_output.weight, self.itm_output.bias, False, False)
+        if compute_loss:
+            return F.cross_entropy(itm_scores.float(), batch["targets"], reduction="none"), None
+        return itm_scores, None
+
+    def forward_mrc(self, batch, task, compute_loss=True):                # model/pretrain.py:201-229
+        packed, meta = self._encode(batch, img_masks=batch["img_masks"])
+        masked_output = _masked_rows(packed, meta, batch["img_mask_tgt"], batch["mrm_index"])
+        prediction_soft_label = self.region_classifier(masked_output)
+        if not compute_loss:
+            return prediction_soft_label
+        label_targets = batch["label_targets"]
+        if "kl" in task:
+            logp = F.log_softmax(prediction_soft_label.float(), dim=-1)
+            return F.kl_div(logp, label_targets.float(), reduction="none")
+        label_targets = torch.max(label_targets[:, 1:], dim=-1)[1] + 1   # background is never a target
+        return F.cross_entropy(prediction_soft_label.float(), label_targets, ignore_index=0, reduction="none")
 
 
 class UniterForVisualQuestionAnswering(UniterPreTrainedModel):

@@ -209,7 +209,8 @@ class BertLayer(nn.Module):
 
 
 class BertPooler(nn.Module):
-    """tanh(dense(x[:, 0])) — model/layer.py:173-185.  [B, H] x [H, H]: negligible, plain torch."""
+    """tanh(dense(x[:, 0])) — model/layer.py:173-185 — on libub200: the [CLS] rows are read in place
+    from the [B, L, H] tensor (row pitch L*H), one tcgen05 GEMM with the bias + tanh epilogue."""
 
     def __init__(self, config):
         super().__init__()
@@ -217,7 +218,8 @@ class BertPooler(nn.Module):
         self.activation = nn.Tanh()
 
     def forward(self, hidden_states):
-        return self.activation(self.dense(hidden_states[:, 0]))
+        first = hidden_states[:, 0] if hidden_states.dim() == 3 else hidden_states
+        return LibLinear.apply(first, self.dense.weight, self.dense.bias, False, True)
 
 
 class UniterTextEmbeddings(nn.Module):
@@ -460,6 +462,81 @@ class _GatherRows(torch.autograd.Function):
             valid = (index >= 0).unsqueeze(1)
             out.index_add_(0, index.clamp(min=0).long(), grad * valid)
         return out.view(ctx.src_shape), None, None, None
+
+
+class LibLinear(torch.autograd.Function):
+    """y = act(x W^T + b) with W [N, K] (an nn.Linear weight, `w_kn` False), or y = act(x W + b) with
+    W [K, N] (`w_kn` True: the reference's `F.linear(h, weight.t(), bias)` of RegionFeatureRegression,
+    model/pretrain.py:29-32, whose weight is the tied img_linear.weight) — forward, dgrad and wgrad on
+    the tcgen05 GEMM (operands read un-transposed in every direction), bias gradient by ub200_colsum.
+    act = tanh when `tanh` (BertPooler).  N may be any size (padded to 8 internally: ITM's 2
+    classes, the 1601 region labels).  Parameters that live in a gradient arena get their gradients
+    written there directly (None is returned to autograd); others are returned normally."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, w_kn, tanh):
+        from . import ops
+        if not x.is_cuda or x.dtype not in (torch.float16, torch.bfloat16):
+            raise RuntimeError("libub200 heads need fp16/bf16 CUDA tensors (no fp32 / CPU fallback)")
+        K = x.size(-1)
+        x2 = x if x.dim() == 2 and x.stride(1) == 1 and x.stride(0) % 8 == 0 else x.reshape(-1, K).contiguous()
+        N = weight.size(1) if w_kn else weight.size(0)
+        Np = (N + 7) // 8 * 8
+        w = weight if weight.is_contiguous() else weight.contiguous()
+        if w_kn and Np != N:
+            raise RuntimeError("LibLinear: a [K, N] weight needs N % 8 == 0")
+        if bias is not None and Np != N:
+            bias_p = torch.zeros(Np, device=x.device, dtype=x.dtype)
+            bias_p[:N] = bias
+        else:
+            bias_p = bias
+        out = torch.empty(x2.size(0), Np, device=x.device, dtype=x.dtype)
+        ops.gemm(x2, w, b_major=1 if w_kn else 0, bias=bias_p, out=out, tanh=bool(tanh),
+                 n_valid=N if Np != N else 0)
+        ctx.save_for_backward(x2, w, out if tanh else None)
+        ctx.meta = (bool(w_kn), bool(tanh), N, Np, weight, bias, x.shape)
+        return out[:, :N] if Np != N else out
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import ops
+        x2, w, y = ctx.saved_tensors
+        w_kn, tanh, N, Np, weight, bias, x_shape = ctx.meta
+        dtype = x2.dtype
+        if Np != N or not dy.is_contiguous():
+            d = torch.zeros(dy.size(0), Np, device=dy.device, dtype=dtype)
+            d[:, :N] = dy
+            dy = d
+        if tanh:
+            dy = ops.dtanh_mul(dy, y)
+        dyv = dy[:, :N]                       # [n, N] view with row pitch Np
+        arena = getattr(weight, "_ub_arena", None)
+        if arena is not None and (id(weight) not in arena._views or not arena._still_valid()):
+            arena = None
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # dx = dy W (w [N, K]: B read as [K=N, N=K] b_major 1)  |  dx = dy W^T (w [K, N]: b_major 0)
+            dx = ops.gemm(dyv, w, b_major=0 if w_kn else 1).view(x_shape)
+        if weight.requires_grad:
+            if arena is not None:
+                arena.mark_managed([weight])
+                acc = arena.claim([weight])
+                tgt = arena.view(weight)
+            else:
+                acc, tgt = False, torch.empty_like(w)
+            if w_kn:      # dW [K, N] = x^T dy
+                ops.gemm(x2, dyv, a_major=1, b_major=1, out=tgt, accumulate=acc)
+            else:         # dW [N, K] = dy^T x
+                ops.gemm(dyv, x2, a_major=1, b_major=1, out=tgt, accumulate=acc)
+            dw = None if arena is not None else tgt
+        if bias is not None and bias.requires_grad:
+            cs = ops.colsum(dy)[:N]
+            if arena is not None and id(bias) in arena._views:
+                arena.mark_managed([bias])
+                ops.cvt_from_f32(cs, dtype, out=arena.view(bias), accumulate=arena.claim([bias]))
+            else:
+                db = ops.cvt_from_f32(cs, dtype)
+        return dx, dw, db, None, None
 
 
 class _EmbedFront(torch.autograd.Function):
@@ -878,7 +955,8 @@ class UniterModel(UniterPreTrainedModel):
         ep["gtable"], ep["small32"] = gtable, small32
         te, ie = self.embeddings, self.img_embeddings
         managed = [q for lp in ep["layer_params"] for q in lp] + ep["front_small_params"] + \
-            [te.word_embeddings.weight, ie.img_linear.weight, ie.mask_embedding.weight]
+            [te.word_embeddings.weight, ie.img_linear.weight, ie.mask_embedding.weight] + \
+            list(self.pooler.parameters())
         arena.mark_managed(managed)
         self._arena = (arena, ep)
 
@@ -1048,7 +1126,10 @@ class UniterModel(UniterPreTrainedModel):
 
 def gather_packed_rows(packed, rows):
     """packed[rows] with zeros where rows < 0 (int32 [n]); differentiable.  The backward is itself
-    a row gather through the inverse map, so neither direction needs atomics or a sync."""
+    a row gather through the inverse map, so neither direction needs atomics or a sync.
+    `rows` must not contain a packed row twice (true for MLM / MRM positions and [CLS] rows): the
+    inverse map keeps one entry per packed row, a duplicate's gradient would be dropped — use
+    `_GatherRows.apply(packed, rows, T, None)` (scatter-add backward) for arbitrary index lists."""
     T = packed.size(0)
     n = rows.numel()
     inv = torch.full((T + 1,), -1, device=packed.device, dtype=torch.int32)

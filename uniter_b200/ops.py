@@ -15,7 +15,7 @@ from ._lib import (EPI_ACCUM, EPI_ATOMIC, EPI_BIAS, EPI_COLSUM, EPI_DGELU, EPI_D
 def gemm(a, b, *, a_major=0, b_major=0, bias=None, residual=None, aux=None, out=None,
          gelu=False, dgelu=False, accumulate=False, out_fp32=False, colsum=None,
          dropout_p=0.0, rng_seed=0, rng_stream=0, tile_n=0, max_ctas=0, cluster=0, k_splits=0,
-         n_valid=0, rng_offset_dev=None, _debug_flags=0):
+         n_valid=0, rng_offset_dev=None, tanh=False, _debug_flags=0):
     """D = epilogue(A . B^T) on the tcgen05 GEMM core.  Returns `out` (and pre-activation if gelu).
 
     a: [M,K] (a_major=0) or [K,M] (a_major=1);  b: [N,K] (b_major=0) or [K,N] (b_major=1).
@@ -53,6 +53,8 @@ def gemm(a, b, *, a_major=0, b_major=0, bias=None, residual=None, aux=None, out=
         epi |= EPI_RESIDUAL
     if gelu:
         epi |= EPI_GELU
+    if tanh:
+        epi |= _lib.EPI_TANH
     if dgelu:
         epi |= EPI_DGELU
     if accumulate:
@@ -206,6 +208,16 @@ def dgelu_mul(dy, pre):
     out = torch.empty_like(dy)
     assert dy.is_contiguous() and pre.is_contiguous() and dy.numel() % 8 == 0
     _lib.check(lib.ub200_dgelu_mul(dy.data_ptr(), pre.data_ptr(), out.data_ptr(), dy.numel(),
+                                   _lib.dtype_code(dy.dtype), _lib.current_stream()))
+    return out
+
+
+def dtanh_mul(dy, y):
+    """dy * (1 - y^2): backward of y = tanh(.) (BertPooler)."""
+    lib = _lib.load()
+    out = torch.empty_like(dy)
+    assert dy.is_contiguous() and y.is_contiguous() and dy.numel() % 8 == 0
+    _lib.check(lib.ub200_dtanh_mul(dy.data_ptr(), y.data_ptr(), out.data_ptr(), dy.numel(),
                                    _lib.dtype_code(dy.dtype), _lib.current_stream()))
     return out
 

@@ -67,21 +67,30 @@ class FusedAdamW(object):
             for k, v in defaults.items():
                 g.setdefault(k, v)
             self.param_groups.append(g)
-        self.state = {}          # id(param) -> dict(step, master, exp_avg, exp_avg_sq)
-        self._step_count = 0
-        self._dev_tables = None  # (segs uint8 tensor, blk_start int32 tensor) on the device
-        self._sumsq = None
+        self.state = {}          # id(param) -> dict(step_offset, master, exp_avg, exp_avg_sq)
+        self._tables = None      # device-resident segment table + bookkeeping (see _build_tables)
+        self._dev_state = None   # int32 [4] on the device: step, found_inf, skipped, pad (ub200_adam_state)
+        self._lr_dev = None
+        self._lr_pinned = None
         self.last_sumsq = None   # device scalar: sum of squares of the (scaled) gradients
-        self._ring = _lib.PinnedRing(8)
 
     # ------------------------------------------------------------------ state
-    def _init_state(self, p):
+    def _init_state(self, p, step_now):
         st = self.state.get(id(p))
         if st is None:
-            st = dict(step=0, master=p.detach().float().clone(),
-                      exp_avg=torch.zeros(p.shape, device=p.device, dtype=torch.float32),
-                      exp_avg_sq=torch.zeros(p.shape, device=p.device, dtype=torch.float32))
+            st = dict(step_offset=step_now)
             self.state[id(p)] = st
+        if "master" not in st:           # e.g. a reference AdamW train_state: step / exp_avg / exp_avg_sq only
+            st["master"] = p.detach().float().clone()
+        for k in ("exp_avg", "exp_avg_sq"):
+            t = st.get(k)
+            if t is None:
+                st[k] = torch.zeros(p.shape, device=p.device, dtype=torch.float32)
+            elif t.dtype != torch.float32 or not t.is_contiguous() or t.device != p.device:
+                st[k] = t.to(device=p.device, dtype=torch.float32).contiguous()
+        m = st["master"]
+        if m.dtype != torch.float32 or not m.is_contiguous() or m.device != p.device:
+            st["master"] = m.to(device=p.device, dtype=torch.float32).contiguous()
         return st
 
     def zero_grad(self, set_to_none=True):
@@ -92,22 +101,43 @@ class FusedAdamW(object):
                 elif p.grad is not None:
                     p.grad.zero_()
 
+    def _applied_steps(self):
+        """Optimizer steps actually applied so far (reads the device counter: synchronises)."""
+        return int(self._dev_state[0].item()) if self._dev_state is not None else 0
+
+    @property
+    def found_inf(self):
+        """Device int32 scalar: 1 iff the last step() saw a non-finite gradient norm and was skipped
+        (what apex's dynamic loss scaler reads to lower the scale) — no host synchronisation."""
+        return None if self._dev_state is None else self._dev_state[1]
+
+    def skipped_steps(self):
+        return int(self._dev_state[2].item()) if self._dev_state is not None else 0
+
     def state_dict(self):
         packed, idx = {}, 0
         groups = []
+        applied = self._applied_steps()
         for g in self.param_groups:
             ids = []
             for p in g["params"]:
                 st = self.state.get(id(p))
                 if st is not None:
-                    packed[idx] = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                    d = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items() if k != "step_offset"}
+                    d["step"] = applied - st.get("step_offset", 0)
+                    packed[idx] = d
                 ids.append(idx)
                 idx += 1
             groups.append({k: (ids if k == "params" else v) for k, v in g.items()})
         return {"state": packed, "param_groups": groups}
 
     def load_state_dict(self, sd):
+        """Accepts its own state_dict and a reference AdamW one (optim/adamw.py: step / exp_avg /
+        exp_avg_sq, possibly 16-bit, no master): masters are rebuilt from the parameters and the
+        moments cast to contiguous fp32 on first use (_init_state)."""
         idx = 0
+        steps = []
+        loaded = []
         for g, sg in zip(self.param_groups, sd["param_groups"]):
             for k, v in sg.items():
                 if k != "params":
@@ -115,24 +145,53 @@ class FusedAdamW(object):
             for p in g["params"]:
                 st = sd["state"].get(idx)
                 if st is not None:
-                    self.state[id(p)] = {k: (v.to(p.device).clone() if torch.is_tensor(v) else v)
-                                         for k, v in st.items()}
+                    d = {k: (v.to(p.device).clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                    steps.append(int(d.pop("step", 0)))
+                    loaded.append((p, d, steps[-1]))
                 idx += 1
+        top = max(steps) if steps else 0
+        for p, d, stp in loaded:
+            d["step_offset"] = top - stp
+            self.state[id(p)] = d
+        self._tables = None
+        if loaded:
+            dev = loaded[0][0].device
+            if dev.type == "cuda":
+                self._dev_state = torch.tensor([top, 0, 0, 0], device=dev, dtype=torch.int32)
 
-    # ------------------------------------------------------------------ step
-    @torch.no_grad()
-    def step(self, grad_scale=1.0, max_grad_norm=-1.0):
-        """One optimizer step over every parameter that has a gradient.
+    # ------------------------------------------------------------------ device tables
+    def _table_key(self):
+        key = []
+        for gi, g in enumerate(self.param_groups):
+            key.append((gi, g["weight_decay"], bool(g["correct_bias"]), tuple(g["betas"]), g["eps"]))
+            for p in g["params"]:
+                if p.grad is not None:
+                    key.append((id(p), p.grad.data_ptr(), p.data_ptr(), p.grad.dtype, p.dtype))
+        return tuple(key)
 
-        grad_scale: the loss scale the gradients carry (they are multiplied by 1 / grad_scale);
-        max_grad_norm > 0: clip the global norm of the unscaled gradients like
-        ``clip_grad_norm_`` (the norm itself stays on the device: ``self.last_sumsq``)."""
+    def _build_tables(self, key):
+        """Segment table (one entry per parameter tensor with a gradient), CTA prefix sums, per-group
+        learning rates and the optimizer state counters, all in DEVICE memory at fixed addresses, so
+        that a step is three launches with constant arguments (capturable in a CUDA graph).  Rebuilt
+        only when the set of (parameter, gradient buffer) pairs changes."""
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("FusedAdamW: the set of gradients changed inside a CUDA-graph capture; run one "
+                               "eager step() first (GraphedStep's warm-up does)")
         lib = _lib.load()
         chunk = lib.ub200_adam_chunk()
-        segs, starts = [], [0]
+        segs, starts, keep = [], [0], []
         dev = None
         betas = eps = None
         for g in self.param_groups:
+            for p in g["params"]:
+                if p.grad is not None:
+                    dev = p.device
+        if dev is None:
+            return None
+        if self._dev_state is None or self._dev_state.device != dev:
+            self._dev_state = torch.zeros(4, device=dev, dtype=torch.int32)
+        step_now = self._applied_steps()
+        for gi, g in enumerate(self.param_groups):
             b1, b2 = g["betas"]
             if betas is None:
                 betas, eps = (b1, b2), g["eps"]
@@ -145,45 +204,82 @@ class FusedAdamW(object):
                     raise RuntimeError("FusedAdamW runs on CUDA parameters only (no CPU fallback)")
                 if p.grad.is_sparse:
                     raise RuntimeError("Adam does not support sparse gradients")
-                if not p.is_contiguous():
-                    raise RuntimeError("FusedAdamW needs contiguous parameters")
-                grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                st = self._init_state(p)
-                st["step"] += 1
-                step_size = g["lr"]
-                if g["correct_bias"]:                                   # optim/adamw.py:82-86
-                    bc1 = 1.0 - b1 ** st["step"]
-                    bc2 = 1.0 - b2 ** st["step"]
-                    step_size = step_size * math.sqrt(bc2) / bc1
-                lr_wd = g["lr"] * g["weight_decay"] if g["weight_decay"] > 0.0 else 0.0
+                if not p.is_contiguous() or not p.grad.is_contiguous():
+                    raise RuntimeError("FusedAdamW needs contiguous parameters and gradients")
+                st = self._init_state(p, step_now)
                 segs.append(_lib.AdamSegment(
-                    grad=grad.data_ptr(), master=st["master"].data_ptr(), exp_avg=st["exp_avg"].data_ptr(),
+                    grad=p.grad.data_ptr(), master=st["master"].data_ptr(), exp_avg=st["exp_avg"].data_ptr(),
                     exp_avg_sq=st["exp_avg_sq"].data_ptr(), model=p.data_ptr(), n=p.numel(),
-                    step_size=step_size, lr_wd=lr_wd,
-                    grad_dtype=_lib.dtype_code(grad.dtype, allow_f32=True),
-                    model_dtype=_lib.dtype_code(p.dtype, allow_f32=True)))
-                segs[-1]._keep = grad
+                    step_size=0.0, lr_wd=0.0,
+                    grad_dtype=_lib.dtype_code(p.grad.dtype, allow_f32=True),
+                    model_dtype=_lib.dtype_code(p.dtype, allow_f32=True),
+                    weight_decay=float(g["weight_decay"]), group=gi, step_offset=int(st["step_offset"]),
+                    flags=1 if g["correct_bias"] else 0))
+                keep.append(p.grad)
                 starts.append(starts[-1] + (p.numel() + chunk - 1) // chunk)
-                dev = p.device
-        if not segs:
-            return None
         nseg, nblocks = len(segs), starts[-1]
         arr = (_lib.AdamSegment * nseg)(*segs)
-        seg_bytes = C.sizeof(arr)
-        host = torch.frombuffer(bytearray(C.string_at(C.addressof(arr), seg_bytes)), dtype=torch.uint8)
-        # pinned staging: a pageable H2D copy here would drain the stream (a sync per step)
-        segs_dev = self._ring.upload(host, dev)
-        starts_dev = self._ring.upload(torch.tensor(starts, dtype=torch.int32), dev)
+        host = torch.frombuffer(bytearray(C.string_at(C.addressof(arr), C.sizeof(arr))), dtype=torch.uint8)
+        segs_dev = host.pin_memory().to(dev, non_blocking=True)
+        starts_dev = torch.tensor(starts, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+        self._lr_dev = torch.zeros(len(self.param_groups), device=dev, dtype=torch.float32)
+        self._lr_pinned = [torch.zeros(len(self.param_groups), dtype=torch.float32).pin_memory() for _ in range(4)]
+        self._lr_slot = 0
+        self._lr_events = [None] * 4
+        self._lr_last = None
+        self.last_sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self._tables = dict(key=key, segs=segs_dev, starts=starts_dev, nseg=nseg, nblocks=nblocks,
+                            betas=betas, eps=eps, keep=keep)
+        return self._tables
+
+    def sync_lr(self):
+        """Ship param_groups[*]['lr'] to the device (the training loop mutates it every step,
+        train_vqa.py:207-214).  step() does this itself except inside a CUDA-graph capture: a captured
+        step reads the learning rate from device memory, so call sync_lr() before each replay."""
+        if self._lr_dev is None:
+            return
+        lrs = [float(g["lr"]) for g in self.param_groups]
+        if lrs == self._lr_last:
+            return
+        k = self._lr_slot
+        self._lr_slot = (k + 1) % len(self._lr_pinned)
+        if self._lr_events[k] is not None:
+            self._lr_events[k].synchronize()
+        self._lr_pinned[k].copy_(torch.tensor(lrs, dtype=torch.float32))
+        self._lr_dev.copy_(self._lr_pinned[k], non_blocking=True)
+        ev = self._lr_events[k] or torch.cuda.Event()
+        ev.record()
+        self._lr_events[k] = ev
+        self._lr_last = lrs
+
+    # ------------------------------------------------------------------ step
+    @torch.no_grad()
+    def step(self, grad_scale=1.0, max_grad_norm=-1.0):
+        """One optimizer step over every parameter that has a gradient: global gradient norm
+        (always — it is also the overflow detector), device-side bookkeeping, fused update.
+
+        grad_scale: the loss scale the gradients carry (they are multiplied by 1 / grad_scale);
+        max_grad_norm > 0: clip the global norm of the unscaled gradients like ``clip_grad_norm_``
+        (the norm itself stays on the device: ``self.last_sumsq``).  A non-finite norm (fp16
+        overflow) SKIPS the step on the device — masters, moments, weights and the step count stay
+        untouched and ``self.found_inf`` is set — like apex's dynamic loss scaler does."""
+        lib = _lib.load()
+        key = self._table_key()
+        T = self._tables
+        if T is None or T["key"] != key:
+            T = self._build_tables(key)
+            if T is None:
+                return None
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()
         stream = _lib.current_stream()
-        sumsq_ptr = None
-        if max_grad_norm is not None and max_grad_norm > 0:
-            self.last_sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
-            _lib.check(lib.ub200_grad_sumsq(segs_dev.data_ptr(), starts_dev.data_ptr(), nseg, nblocks,
-                                            self.last_sumsq.data_ptr(), stream))
-            sumsq_ptr = self.last_sumsq.data_ptr()
-        _lib.check(lib.ub200_adamw_step(segs_dev.data_ptr(), starts_dev.data_ptr(), nseg, nblocks,
-                                        betas[0], betas[1], eps, 1.0 / float(grad_scale),
-                                        float(max_grad_norm) if sumsq_ptr else -1.0, sumsq_ptr, stream))
-        self._dev_tables = (segs_dev, starts_dev)   # keep alive until the kernels have run
-        self._step_count += 1
+        self.last_sumsq.zero_()
+        _lib.check(lib.ub200_grad_sumsq(T["segs"].data_ptr(), T["starts"].data_ptr(), T["nseg"], T["nblocks"],
+                                        self.last_sumsq.data_ptr(), stream))
+        _lib.check(lib.ub200_adam_prep(self.last_sumsq.data_ptr(), self._dev_state.data_ptr(), stream))
+        clip = max_grad_norm is not None and max_grad_norm > 0
+        _lib.check(lib.ub200_adamw_step(T["segs"].data_ptr(), T["starts"].data_ptr(), T["nseg"], T["nblocks"],
+                                        T["betas"][0], T["betas"][1], T["eps"], 1.0 / float(grad_scale),
+                                        float(max_grad_norm) if clip else -1.0, self.last_sumsq.data_ptr(),
+                                        self._dev_state.data_ptr(), self._lr_dev.data_ptr(), stream))
         return None

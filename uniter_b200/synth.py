@@ -148,3 +148,49 @@ def pad_mlm_index(batch, multiple=64):
     out["mlm_targets"] = torch.cat([tgt, torch.full((n_pad - n,), -1, dtype=tgt.dtype)])
     out["mlm_inv_n"] = torch.tensor([1.0 / max(n, 1)], dtype=torch.float32)
     return out
+
+
+def synth_mrm(batch, mask_prob=0.15, label_dim=1601, seed=0, pad_multiple=0):
+    """MRM inputs on top of a synth_batch, with the semantics of data/mrm.py: per-region Bernoulli
+    mask with at least one masked region per sample (:14-20), `img_mask_tgt` over the joint [B, L]
+    layout (:23-26), `feat_targets` = the original features of the masked regions (:29-34), the
+    masked regions' input features zeroed (:37-40), and soft labels `label_targets` [n, label_dim]
+    (data/mrm.py:157-163: the detector's class distribution; here softmax of N(0, 1)).
+    `mrm_index` = flat positions b * L + j of the masked regions (host-side compaction: what
+    `_compute_masked_hidden`, model/pretrain.py:129-133, extracts with a device-side boolean mask);
+    with `pad_multiple` it is padded with B * L and the targets with zero rows, and `mrm_valid` [n]
+    marks the real rows."""
+    g = torch.Generator().manual_seed(seed)
+    img_feat = batch["img_feat"]
+    B, Li, D = img_feat.shape
+    L = batch["attn_masks"].size(1)
+    img_masks = torch.zeros(B, Li, dtype=torch.bool)
+    img_mask_tgt = torch.zeros(B, L, dtype=torch.bool)
+    for i, (tl, nbb) in enumerate(zip(batch["txt_lens"], batch["num_bbs"])):
+        m = torch.rand(nbb, generator=g) < mask_prob
+        if not m.any():
+            m[int(torch.randint(0, nbb, (1,), generator=g))] = True
+        img_masks[i, :nbb] = m
+        img_mask_tgt[i, tl:tl + nbb] = m
+    feat_targets = img_feat[img_masks].contiguous()
+    n = feat_targets.size(0)
+    out = dict(batch)
+    out["img_feat"] = img_feat.masked_fill(img_masks.unsqueeze(-1), 0)
+    out["img_masks"] = img_masks
+    out["img_mask_tgt"] = img_mask_tgt
+    out["feat_targets"] = feat_targets
+    out["label_targets"] = torch.softmax(torch.randn(n, label_dim, generator=g), dim=-1)
+    pos = img_mask_tgt.nonzero(as_tuple=False)
+    idx = (pos[:, 0] * L + pos[:, 1]).contiguous()
+    valid = torch.ones(n, dtype=torch.float32)
+    if pad_multiple:
+        n_pad = max((n + pad_multiple - 1) // pad_multiple * pad_multiple, pad_multiple)
+        idx = torch.cat([idx, torch.full((n_pad - n,), B * L, dtype=idx.dtype)])
+        out["feat_targets"] = torch.cat([feat_targets, torch.zeros(n_pad - n, D)])
+        out["label_targets"] = torch.cat([out["label_targets"],
+                                          torch.full((n_pad - n, label_dim), 1.0 / label_dim)])
+        valid = torch.cat([valid, torch.zeros(n_pad - n)])
+    out["mrm_index"] = idx
+    out["mrm_valid"] = valid
+    out["mrm_inv_n"] = torch.tensor([1.0 / max(n, 1)], dtype=torch.float32)
+    return out
