@@ -251,6 +251,121 @@ def run_batching(out_path):
     print("wrote", out_path, "%.1f KB" % (os.path.getsize(out_path) / 1024))
 
 
+class FakeTxtDB(object):
+    """In-memory stand-in for TxtTokLmdb (data/data.py:176-230): only what the ITM datasets use."""
+
+    def __init__(self, texts, txt2img, img2txts):
+        self.texts, self.txt2img, self.img2txts = texts, txt2img, img2txts
+        self.cls_, self.sep = 101, 102
+
+    def __getitem__(self, id_):
+        return {"input_ids": list(self.texts[id_])}
+
+    def combine_inputs(self, *inputs):
+        input_ids = [self.cls_]
+        for ids in inputs:
+            input_ids.extend(ids + [self.sep])
+        return torch.tensor(input_ids)
+
+
+class FakeImgDB(object):
+    """Stand-in for DetectFeatLmdb: fname -> (feat [n, D], bb [n, 6] = x1,y1,x2,y2,w,h)."""
+
+    def __init__(self, items):
+        self.items = items
+
+    def __getitem__(self, fname):
+        return self.items[fname]
+
+
+def itm_world(seed=5, n_img=9, txt_per_img=2, D=16):
+    """A tiny seeded retrieval corpus: images, their captions, and the id maps the datasets use."""
+    g = torch.Generator().manual_seed(seed)
+    imgs, texts, txt2img, img2txts = {}, {}, {}, {}
+    for i in range(n_img):
+        fname = "img%02d" % i
+        nbb = int(torch.randint(2, 8, (1,), generator=g))
+        xy = torch.rand(nbb, 4, generator=g)
+        bb = torch.cat([xy, (xy[:, 2:3] - xy[:, 0:1]).abs(), (xy[:, 3:4] - xy[:, 1:2]).abs()], 1)
+        imgs[fname] = (torch.randn(nbb, D, generator=g), bb)
+        img2txts[fname] = []
+        for j in range(txt_per_img):
+            tid = "t%02d_%d" % (i, j)
+            tl = int(torch.randint(2, 8, (1,), generator=g))
+            texts[tid] = torch.randint(1000, 2000, (tl,), generator=g).tolist()
+            txt2img[tid] = fname
+            img2txts[fname].append(tid)
+    return FakeTxtDB(texts, txt2img, img2txts), FakeImgDB(imgs), sorted(texts.keys())
+
+
+def mrm_samples(seed, n, soft, D=16, C=5):
+    """Per-sample tuples as MrfrDataset / MrcDataset.__getitem__ return them (data/mrm.py:48-73,
+    :141-173)."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        tl = int(torch.randint(3, 9, (1,), generator=g))
+        nb = int(torch.randint(2, 7, (1,), generator=g))
+        ids = torch.randint(1000, 2000, (tl,), generator=g)
+        f, p = torch.randn(nb, D, generator=g), torch.rand(nb, 7, generator=g)
+        am = torch.ones(tl + nb, dtype=torch.long)
+        m = torch.rand(nb, generator=g) < 0.4
+        m[int(torch.randint(0, nb, (1,), generator=g))] = True
+        tgt = torch.cat([torch.zeros(tl, dtype=torch.uint8), m.to(torch.uint8)])
+        if soft:
+            out.append((ids, f, p, torch.softmax(torch.randn(nb, C, generator=g), -1), am, m, tgt))
+        else:
+            out.append((ids, f, p, am, m, tgt))
+    return out
+
+
+def rank_samples(seed, n_anchor, n_pair, D=16):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n_anchor):
+        pairs = []
+        for _ in range(n_pair):
+            tl = int(torch.randint(3, 9, (1,), generator=g))
+            nb = int(torch.randint(2, 7, (1,), generator=g))
+            pairs.append((torch.randint(1000, 2000, (tl,), generator=g), torch.randn(nb, D, generator=g),
+                          torch.rand(nb, 7, generator=g), torch.ones(tl + nb, dtype=torch.long)))
+        out.append(pairs)
+    return out
+
+
+def run_itm_batching(out_path):
+    """The reference's own ITM-ranking / MRM batch builders (data/itm.py:240-374, data/mrm.py:76-227)
+    on seeded in-memory stores: itm_rank_collate, the two hard-negative datasets' __getitem__
+    (negatives drawn from the global `random` state), mrfr_collate, mrc_collate."""
+    import random
+    import_reference_data()
+    import data.itm as ritm
+    import data.mrm as rmrm
+    rec = {}
+
+    def put(prefix, batch):
+        for k, v in batch.items():
+            rec["%s/%s" % (prefix, k)] = v.numpy() if torch.is_tensor(v) else np.array(v)
+
+    put("rank", ritm.itm_rank_collate(rank_samples(41, 3, 3)))
+    txt_db, img_db, ids = itm_world()
+    for name, cls in (("hn_t", ritm.ItmRankDatasetHardNegFromText), ("hn_i", ritm.ItmRankDatasetHardNegFromImage)):
+        ds = object.__new__(cls)                      # skip the LMDB-typed constructor
+        ds.txt_db, ds.img_db, ds.ids = txt_db, img_db, ids
+        ds.txt2img = {i: txt_db.txt2img[i] for i in ids}
+        ds.img2txts = txt_db.img2txts
+        ds.img_name_list = list(ds.img2txts.keys())
+        ds.txt_name_list = list(ds.txt2img.keys())
+        ds.neg_sample_size = 4
+        for i in (0, 7):
+            random.seed(100 + i)
+            put("%s%d" % (name, i), ritm.itm_rank_hn_collate([ds[i]]))
+    put("mrfr", rmrm.mrfr_collate(mrm_samples(51, 5, False)))
+    put("mrc", rmrm.mrc_collate(mrm_samples(52, 5, True)))
+    np.savez_compressed(out_path, **rec)
+    print("wrote", out_path, "%.1f KB" % (os.path.getsize(out_path) / 1024))
+
+
 def hardneg_inputs(sample_from, seed):
     """A 9-pair hard-negative batch as data/itm.py:270-361 builds it (one text x 9 images, or one
     image x 9 texts), plus random pair scores."""
@@ -386,6 +501,7 @@ def main():
     run_hardneg(rm, os.path.join(HERE, "hardneg.npz"))
     run_adamw(os.path.join(HERE, "adamw.npz"))
     run_batching(os.path.join(HERE, "batching.npz"))
+    run_itm_batching(os.path.join(HERE, "itm_batching.npz"))
 
 
 if __name__ == "__main__":

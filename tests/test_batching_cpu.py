@@ -75,3 +75,44 @@ def test_empty_and_single_sample_edges():
     assert b["cu_seqlens"].tolist() == [0, one[0][0].numel() + one[0][1].size(0)]
     # a sampler over zero samples yields no batches
     assert list(iter(batching.TokenBucketSampler([], 8, 64))) == []
+
+
+def test_itm_rank_and_mrm_batch_builders_match_reference_bit_exactly():
+    """data/itm.py:240-374 (itm_rank_collate, the two hard-negative datasets incl. the stale-`tl`
+    gather_index of :356-361, itm_rank_hn_collate) and data/mrm.py:76-227 (mrfr / mrc collates)
+    against outputs of the reference's own code (tests/golden/itm_batching.npz)."""
+    from tests.golden.make_goldens import itm_world, mrm_samples, rank_samples
+    g = util.load_golden("itm_batching")
+
+    def check(prefix, batch):
+        keys = [k[len(prefix) + 1:] for k in g if k.startswith(prefix + "/")]
+        assert len(keys) >= 6, prefix
+        for k in keys:
+            ref = g["%s/%s" % (prefix, k)]
+            got = batch[k]
+            if torch.is_tensor(got):
+                assert got.dtype == torch.from_numpy(ref).dtype, (prefix, k)
+                assert np.array_equal(got.numpy(), ref), (prefix, k)
+            else:
+                assert np.array_equal(np.array(got), ref), (prefix, k)
+
+    check("rank", batching.itm_rank_collate(rank_samples(41, 3, 3)))
+    txt_db, img_db, ids = itm_world()
+    for name, cls in (("hn_t", batching.ItmRankDatasetHardNegFromText),
+                      ("hn_i", batching.ItmRankDatasetHardNegFromImage)):
+        ds = cls(txt_db, img_db, ids, txt_db.txt2img, txt_db.img2txts, neg_sample_size=4)
+        for i in (0, 7):
+            random.seed(100 + i)
+            b = batching.itm_rank_hn_collate([ds[i]])
+            check("%s%d" % (name, i), b)
+            lens = [a + c for a, c in zip(b["txt_lens"], b["num_bbs"])]
+            assert b["attn_masks"].sum(1).tolist() == lens            # host bookkeeping for the packed path
+    check("mrfr", batching.mrfr_collate(mrm_samples(51, 5, False)))
+    mb = batching.mrc_collate(mrm_samples(52, 5, True))
+    check("mrc", mb)
+    # mrm_index = flat positions of the masked regions, in the reference's row order
+    L = mb["attn_masks"].size(1)
+    flat = torch.zeros(mb["attn_masks"].numel(), dtype=torch.bool)
+    flat[mb["mrm_index"]] = True
+    assert torch.equal(flat.view(-1, L), mb["img_mask_tgt"].bool())
+    assert mb["label_targets"].size(0) == mb["mrm_index"].numel()

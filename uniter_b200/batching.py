@@ -174,3 +174,179 @@ class DevicePrefetcher(object):
             except StopIteration:
                 nxt = None
             yield batch
+
+
+# ============================================================================ MRM collates
+def _mrm_fields(input_ids, img_feats, img_pos_feats, attn_masks, img_masks, img_mask_tgts):
+    """Common part of data/mrm.py:76-123 (mrfr_collate) and :176-227 (mrc_collate): pad, build the
+    joint fields, extract the masked regions' targets, zero the masked input features."""
+    batch = _joint_fields(input_ids, img_feats, img_pos_feats, attn_masks)
+    img_masks = pad_sequence(img_masks, batch_first=True, padding_value=0)
+    img_mask_tgt = pad_sequence(img_mask_tgts, batch_first=True, padding_value=0)
+    batch["img_masks"] = img_masks
+    batch["img_mask_tgt"] = img_mask_tgt
+    # host-side compaction of the masked positions (flat b * L + j), the fixed-shape stand-in for
+    # `_compute_masked_hidden` (model/pretrain.py:129-133)
+    L = batch["attn_masks"].size(1)
+    pos = img_mask_tgt.nonzero(as_tuple=False)
+    batch["mrm_index"] = (pos[:, 0] * L + pos[:, 1]).contiguous()
+    return batch, img_masks
+
+
+def mrfr_collate(inputs):
+    """inputs: list of (input_ids, img_feat, img_pos_feat, attn_masks, img_mask [nbb] bool,
+    img_mask_tgt [tl + nbb]) — data/mrm.py:76-123."""
+    input_ids, img_feats, img_pos_feats, attn_masks, img_masks, img_mask_tgts = map(list, zip(*inputs))
+    batch, img_masks = _mrm_fields(input_ids, img_feats, img_pos_feats, attn_masks, img_masks, img_mask_tgts)
+    img_feat = batch["img_feat"]
+    ext = img_masks.unsqueeze(-1).expand_as(img_feat)
+    batch["feat_targets"] = img_feat[ext].contiguous().view(-1, img_feat.size(-1))   # data/mrm.py:29-34
+    batch["img_feat"] = img_feat.data.masked_fill(ext, 0)                            # :37-40
+    return batch
+
+
+def mrc_collate(inputs):
+    """inputs: list of (input_ids, img_feat, img_pos_feat, img_soft_labels [nbb, C], attn_masks,
+    img_mask, img_mask_tgt) — data/mrm.py:176-227."""
+    (input_ids, img_feats, img_pos_feats, img_soft_labels, attn_masks, img_masks,
+     img_mask_tgts) = map(list, zip(*inputs))
+    batch, img_masks = _mrm_fields(input_ids, img_feats, img_pos_feats, attn_masks, img_masks, img_mask_tgts)
+    num_bbs = batch["num_bbs"]
+    img_soft_label = pad_tensors(img_soft_labels, num_bbs)
+    ext_l = img_masks.unsqueeze(-1).expand_as(img_soft_label)
+    batch["label_targets"] = img_soft_label[ext_l].contiguous().view(-1, img_soft_label.size(-1))
+    ext = img_masks.unsqueeze(-1).expand_as(batch["img_feat"])
+    batch["img_feat"] = batch["img_feat"].data.masked_fill(ext, 0)
+    return batch
+
+
+# ============================================================================ ITM ranking batches
+def sample_negative(sample_pool, ground_truths, num_sample, rng=None):
+    """data/itm.py:36-46 — random.sample and retry until disjoint from the ground truths."""
+    rng = rng if rng is not None else _random
+    outputs = ground_truths[:1]
+    while set(outputs) & set(ground_truths):
+        outputs = rng.sample(sample_pool, num_sample)
+    return outputs
+
+
+def itm_rank_collate(inputs):
+    """inputs: list (one entry per anchor) of lists of (input_ids, img_feat, img_pos_feat,
+    attn_masks) — positive pair first, then the negatives (data/itm.py:240-269)."""
+    flat = [t for sample in inputs for t in sample]
+    input_ids, img_feats, img_pos_feats, attn_masks = map(list, zip(*flat))
+    batch = _joint_fields(input_ids, img_feats, img_pos_feats, attn_masks)
+    sample_size = len(inputs[0])
+    assert all(sample_size == len(i) for i in inputs)
+    batch["sample_size"] = sample_size
+    return batch
+
+
+def hard_neg_batch_from_text(input_ids, img_feats, img_pos_feats):
+    """One text against 1 + N images, ground truth first (ItmRankDatasetHardNegFromText.__getitem__,
+    data/itm.py:282-320).  input_ids [tl]; img_feats / img_pos_feats: lists of [nbb_i, D] / [nbb_i, 7]."""
+    input_ids = input_ids.unsqueeze(0)
+    position_ids = torch.arange(0, input_ids.size(1), dtype=torch.long).unsqueeze(0)
+    num_bbs = [f.size(0) for f in img_feats]
+    img_feat = pad_tensors(img_feats, num_bbs)
+    img_pos_feat = pad_tensors(img_pos_feats, num_bbs)
+    tl = input_ids.size(1)
+    n = len(img_feats)
+    attn_masks = torch.zeros(n, max(num_bbs) + tl).long()
+    for i, nbb in enumerate(num_bbs):
+        attn_masks.data[i, :tl + nbb].fill_(1)
+    gather_index = get_gather_index([tl] * n, num_bbs, n, tl, attn_masks.size(1))
+    return {"input_ids": input_ids, "position_ids": position_ids, "img_feat": img_feat,
+            "img_pos_feat": img_pos_feat, "attn_masks": attn_masks, "gather_index": gather_index,
+            "txt_lens": [tl] * n, "num_bbs": num_bbs}
+
+
+def hard_neg_batch_from_image(img_feat, img_pos_feat, all_input_ids):
+    """One image against 1 + N texts, ground truth first (ItmRankDatasetHardNegFromImage.__getitem__,
+    data/itm.py:323-369).  Reproduces the reference's gather_index EXACTLY, including its use of the
+    loop variable `tl` left over from the last text as `max_len` (data/itm.py:356-361): image slots
+    then index rows relative to the LAST text's length instead of the padded text length — the
+    drop-in encoder honours whatever index arrives."""
+    nbb = img_feat.size(0)
+    img_feat = img_feat.unsqueeze(0)
+    img_pos_feat = img_pos_feat.unsqueeze(0)
+    txt_lens = [len(i) for i in all_input_ids]
+    input_ids = pad_sequence(all_input_ids, batch_first=True, padding_value=0)
+    position_ids = torch.arange(0, input_ids.size(1), dtype=torch.long).unsqueeze(0)
+    n = len(all_input_ids)
+    attn_masks = torch.zeros(n, max(txt_lens) + nbb).long()
+    for i, tl in enumerate(txt_lens):
+        attn_masks.data[i, :tl + nbb].fill_(1)
+    stale_tl = txt_lens[-1]
+    gather_index = get_gather_index(txt_lens, [nbb] * n, n, stale_tl, attn_masks.size(1))
+    return {"input_ids": input_ids, "position_ids": position_ids, "img_feat": img_feat,
+            "img_pos_feat": img_pos_feat, "attn_masks": attn_masks, "gather_index": gather_index,
+            "txt_lens": txt_lens, "num_bbs": [nbb] * n}
+
+
+def itm_rank_hn_collate(inputs):
+    """data/itm.py:372-374."""
+    assert len(inputs) == 1
+    return inputs[0]
+
+
+def _img_feat_of(img_db, fname):
+    """DetectFeatTxtTokDataset._get_img_feat (data/data.py:247-251): 7-d box = (x1,y1,x2,y2,w,h,w*h)."""
+    img_feat, bb = img_db[fname]
+    img_bb = torch.cat([bb, bb[:, 4:5] * bb[:, 5:]], dim=-1)
+    return img_feat, img_bb, img_feat.size(0)
+
+
+class ItmRankDatasetHardNegFromText(object):
+    """data/itm.py:282-320 over duck-typed stores: `txt_db[id]['input_ids']` (list of token ids),
+    `txt_db.combine_inputs(ids)` ([CLS] ids [SEP] tensor), `img_db[fname] -> (feat [n, D], bb [n, 6])`.
+    Negatives are drawn with the global `random` state exactly like the reference."""
+
+    def __init__(self, txt_db, img_db, ids, txt2img, img2txts, neg_sample_size=1, rng=None):
+        assert neg_sample_size > 0, "need at least 1 negative sample"
+        self.txt_db, self.img_db, self.ids = txt_db, img_db, list(ids)
+        self.txt2img = {id_: txt2img[id_] for id_ in self.ids}
+        self.img2txts = img2txts
+        self.img_name_list = list(self.img2txts.keys())
+        self.neg_sample_size = neg_sample_size
+        self.rng = rng
+
+    def __len__(self):
+        return len(self.ids)
+
+    def __getitem__(self, i):
+        gt_txt_id = self.ids[i]
+        gt_img_fname = self.txt2img[gt_txt_id]
+        input_ids = self.txt_db.combine_inputs(self.txt_db[gt_txt_id]["input_ids"])
+        neg_img_ids = sample_negative(self.img_name_list, [gt_img_fname], self.neg_sample_size, self.rng)
+        feats, boxes = [], []
+        for fname in [gt_img_fname] + neg_img_ids:
+            f, b, _ = _img_feat_of(self.img_db, fname)
+            feats.append(f)
+            boxes.append(b)
+        return hard_neg_batch_from_text(input_ids, feats, boxes)
+
+
+class ItmRankDatasetHardNegFromImage(object):
+    """data/itm.py:323-369 (see hard_neg_batch_from_image for the gather_index quirk it keeps)."""
+
+    def __init__(self, txt_db, img_db, ids, txt2img, img2txts, neg_sample_size=1, rng=None):
+        assert neg_sample_size > 0, "need at least 1 negative sample"
+        self.txt_db, self.img_db, self.ids = txt_db, img_db, list(ids)
+        self.txt2img = {id_: txt2img[id_] for id_ in self.ids}
+        self.img2txts = img2txts
+        self.txt_name_list = list(self.txt2img.keys())
+        self.neg_sample_size = neg_sample_size
+        self.rng = rng
+
+    def __len__(self):
+        return len(self.ids)
+
+    def __getitem__(self, i):
+        gt_txt_id = self.ids[i]
+        gt_img_id = self.txt2img[gt_txt_id]
+        gt_txt_ids = self.img2txts[gt_img_id]
+        img_feat, img_pos_feat, _ = _img_feat_of(self.img_db, gt_img_id)
+        neg_txt_ids = sample_negative(self.txt_name_list, gt_txt_ids, self.neg_sample_size, self.rng)
+        all_inputs = [self.txt_db.combine_inputs(self.txt_db[t]["input_ids"]) for t in [gt_txt_id] + neg_txt_ids]
+        return hard_neg_batch_from_image(img_feat, img_pos_feat, all_inputs)
