@@ -28,7 +28,19 @@ import torch  # noqa: E402
 
 METRIC = "uniter_base_encoder_fwd_bwd_samples_per_sec"
 BASE = dict(vocab=28996, H=768, NL=12, heads=12, I=3072, max_pos=512, img_dim=2048)
+LARGE = dict(vocab=28996, H=1024, NL=24, heads=16, I=4096, max_pos=512, img_dim=2048)
 C2 = dict(B=64, tl=(12, 28), nbb=(26, 46), seed=1234, mlm_prob=0.15)
+# BASELINE.json configs.  The default (and the driver's) run is C2, the config the
+# metric is quoted on; the others are reachable with --config for the profiles / docs.
+CONFIGS = {
+    "c2": dict(label="C2", arch=BASE, arch_name="UNITER-base", metric=METRIC, tasks=("mlm",),
+               B=64, tl=(12, 28), nbb=(26, 46), seed=1234, mlm_prob=0.15, mrm_prob=0.15),
+    "c4": dict(label="C4", arch=LARGE, arch_name="UNITER-large",
+               metric="uniter_large_pretrain_fwd_bwd_samples_per_sec",
+               tasks=("mlm", "mrfr", "mrc-kl", "itm"),
+               B=64, tl=(12, 28), nbb=(26, 46), seed=1234, mlm_prob=0.15, mrm_prob=0.15),
+}
+IMG_LABEL_DIM = 1601
 
 
 def parse():
@@ -50,7 +62,10 @@ def parse():
                     help="enqueue every step from Python (eager) instead of replaying CUDA graphs")
     ap.add_argument("--token-bucket", type=int, default=128,
                     help="graph mode: token counts are padded to a multiple of this with a dummy sequence")
-    ap.add_argument("--layers", type=int, default=BASE["NL"], help=argparse.SUPPRESS)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS),
+                    help="c2 (default, the metric's config): UNITER-base MLM; c4: UNITER-large 24-layer "
+                         "pre-training step, tasks cycled mlm -> mrfr -> mrc-kl -> itm")
+    ap.add_argument("--layers", type=int, default=0, help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -147,7 +162,7 @@ def cpu_reference_run(args, steps, warmup, sample_B):
     are absent, the clean-room oracle port (kind "port")."""
     from oracle import ref_loader
     from uniter_b200.synth import seeded_state, synth_batch
-    NL = args.layers
+    NL = args.layers or BASE["NL"]
     full = synth_batch(C2["B"], C2["tl"][0], C2["tl"][1], C2["nbb"][0], C2["nbb"][1], C2["seed"],
                        mlm_prob=C2["mlm_prob"])
     if sample_B >= C2["B"]:
@@ -233,7 +248,7 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "C2: UNITER-base %d-layer encoder fwd+bwd + MLM head (15%% text masked), "
                                        "B=%d, the reference's own CPU path (%s), train mode dropout 0.1"
-                                       % (args.layers, r["batch"], r["kind"]),
+                                       % (args.layers or BASE["NL"], r["batch"], r["kind"]),
                            "global_batch": r["batch"], "parallelism": "cpu"},
                 "cpu_baseline": cb,
                 "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
@@ -259,51 +274,83 @@ def main():
     _lib.check(lib.ub200_device_check())
     lib.ub200_launch_count.restype = C.c_ulonglong
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
-    NL = args.layers
+    CF = CONFIGS[args.config]
+    ARCH = CF["arch"]
+    NL = args.layers or ARCH["NL"]
+    tasks = CF["tasks"]
 
     torch.manual_seed(0)
-    cfg = UniterConfig(BASE["vocab"], hidden_size=BASE["H"], num_hidden_layers=NL,
-                       num_attention_heads=BASE["heads"], intermediate_size=BASE["I"],
-                       max_position_embeddings=BASE["max_pos"])
-    model = UniterForMLM(cfg, BASE["img_dim"]).to(device=dev, dtype=dtype).train()
+    cfg = UniterConfig(ARCH["vocab"], hidden_size=ARCH["H"], num_hidden_layers=NL,
+                       num_attention_heads=ARCH["heads"], intermediate_size=ARCH["I"],
+                       max_position_embeddings=ARCH["max_pos"])
+    if tasks == ("mlm",):
+        model = UniterForMLM(cfg, ARCH["img_dim"])
+    else:
+        from uniter_b200.heads import UniterForPretraining
+        model = UniterForPretraining(cfg, ARCH["img_dim"], IMG_LABEL_DIM)
+    model = model.to(device=dev, dtype=dtype).train()
     if world > 1:
         ubd.broadcast_parameters(model, root=0)
     GradArena.attach(model)          # one flat gradient buffer: head | pooler | layers | front-end
     reducer = (ubd.GradientReducer(model, overlap_chunks=args.overlap_chunks, sm_reserve=args.sm_reserve)
                if world > 1 else None)
 
-    # ---- synthetic batches (per-rank seed), host side pinned; masked-token lists padded to a
-    # multiple of 64 so that every batch of a token bucket replays the same graph
-    n_host = 4
+    # ---- synthetic batches (per-rank seed), host side pinned; masked-token / masked-region lists are
+    # padded to a multiple of 64 so that every batch of a token bucket replays the same graph.
+    # One task per step, cycled (what MetaLoader does, data/loader.py:39-57).
+    from uniter_b200.synth import synth_mrm
+    n_host = 4 * len(tasks)
     host = []
     for i in range(n_host):
-        b = synth_batch(C2["B"], C2["tl"][0], C2["tl"][1], C2["nbb"][0], C2["nbb"][1],
-                        C2["seed"] + 1000 * rank + (i if i else 0), mlm_prob=C2["mlm_prob"])
-        b = pad_mlm_index(b, 64)
+        task = tasks[i % len(tasks)]
+        b = synth_batch(CF["B"], CF["tl"][0], CF["tl"][1], CF["nbb"][0], CF["nbb"][1],
+                        CF["seed"] + 1000 * rank + (i // len(tasks)), mlm_prob=CF["mlm_prob"])
+        lens = [a + c for a, c in zip(b["txt_lens"], b["num_bbs"])]
+        if task == "mlm":
+            b = pad_mlm_index(b, 64)
+        else:
+            b = {k: v for k, v in b.items() if k not in ("txt_labels", "mlm_index", "mlm_targets")}
+            if task in ("mrfr", "mrc-kl"):
+                b = synth_mrm(b, CF["mrm_prob"], IMG_LABEL_DIM, seed=i, pad_multiple=64)
+                for k in ("img_mask_tgt", "feat_targets" if task != "mrfr" else "label_targets"):
+                    b.pop(k)                                    # only what this task's head reads travels
+            elif task == "itm":
+                b["targets"] = torch.randint(0, 2, (CF["B"],), generator=torch.Generator().manual_seed(i))
         hb = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()}
-        hb["lens"] = [a + c for a, c in zip(b["txt_lens"], b["num_bbs"])]
+        hb["lens"], hb["task"] = lens, task
         host.append(hb)
     lens0 = host[0]["lens"]
-    tensor_keys = [k for k, v in host[0].items() if torch.is_tensor(v)]
-    h2d_bytes = sum(host[0][k].numel() * host[0][k].element_size() for k in tensor_keys)
+    h2d_bytes = sum(sum(v.numel() * v.element_size() for v in hb.values() if torch.is_tensor(v))
+                    for hb in host) // n_host
 
-    def loss_fn(batch):
-        # the reference's `loss.mean()` over the masked tokens (pretrain.py:297) with a fixed-size
-        # (padded) token list: padding rows contribute 0, the divisor is the true count
-        return (model(batch).sum() * batch["mlm_inv_n"]).squeeze()
+    def loss_fn(batch, task):
+        """The scalar the reference's loop back-propagates: `loss.mean()` (pretrain.py:297) — with
+        fixed-size (padded) row lists the padding rows contribute 0 and the divisor is the true count."""
+        if task == "mlm":
+            per_row = model(batch) if tasks == ("mlm",) else model(batch, "mlm")
+            return (per_row.sum() * batch["mlm_inv_n"]).squeeze()
+        if task == "mrfr":
+            l = model(batch, "mrfr").float()                                  # [n_pad, D]
+            return ((l * batch["mrm_valid"].unsqueeze(1)).sum() * batch["mrm_inv_n"] / l.size(1)).squeeze()
+        if task == "mrc-kl":
+            l = model(batch, "mrc-kl").float()                                # [n_pad, labels]
+            return ((l * batch["mrm_valid"].unsqueeze(1)).sum() * batch["mrm_inv_n"] / l.size(1)).squeeze()
+        if task == "itm":
+            return model(batch, "itm")[0].mean()
+        raise ValueError(task)
 
     graphed = None if args.no_graph else GraphedStep(model, loss_fn, token_bucket=args.token_bucket,
                                                      reducer=reducer)
 
     def to_device(hb, stream):
         with torch.cuda.stream(stream):
-            d = {k: hb[k].to(dev, non_blocking=True) for k in tensor_keys}
+            d = {k: v.to(dev, non_blocking=True) for k, v in hb.items() if torch.is_tensor(v)}
         return d
 
-    def eager_step(batch, lens):
+    def eager_step(batch, lens, task):
         register_lengths(batch["attn_masks"], lens, prefix=True)
         model.zero_grad(set_to_none=True)
-        loss = loss_fn(batch)
+        loss = loss_fn(batch, task)
         if reducer is not None:
             reducer.backward_and_reduce(loss)
         else:
@@ -331,17 +378,19 @@ def main():
         return ms
 
     # ---- resident-input measurement ("value"): inputs already in HBM, the step is replayed
-    resident = to_device(host[0], torch.cuda.current_stream())
+    # (one resident batch per task, cycled)
+    nt = len(tasks)
+    resident = [to_device(host[i], torch.cuda.current_stream()) for i in range(nt)]
     torch.cuda.synchronize()
     if graphed is not None:
-        bk0 = graphed.stage(resident, lens0)          # captures the bucket of batch 0 (untimed)
+        bks = [graphed.stage(resident[i], host[i]["lens"], tag=tasks[i]) for i in range(nt)]   # captures (untimed)
         for i in range(args.warmup):
-            bk0.graph.replay()
-        step_resident = lambda i: bk0.graph.replay()  # noqa: E731
+            bks[i % nt].graph.replay()
+        step_resident = lambda i: bks[i % nt].graph.replay()  # noqa: E731
     else:
         for i in range(args.warmup):
-            eager_step(resident, lens0)
-        step_resident = lambda i: eager_step(resident, lens0)  # noqa: E731
+            eager_step(resident[i % nt], host[i % nt]["lens"], tasks[i % nt])
+        step_resident = lambda i: eager_step(resident[i % nt], host[i % nt]["lens"], tasks[i % nt])  # noqa: E731
     torch.cuda.synchronize()
     launches0 = lib.ub200_launch_count()
     sampler = ClockSampler(local_rank)
@@ -357,11 +406,11 @@ def main():
     ms_total = timed(timed_step, args.steps)
     cpu_enqueue_ms = cpu_t[0] / args.steps * 1e3   # host time to enqueue one step (no sync inside)
     if graphed is not None:
-        launches = bk0.launches                    # libub200 kernels inside one replay of the graph
+        launches = sum(b.launches for b in bks) // nt     # libub200 kernels inside one replay of a graph
     else:
         launches = (lib.ub200_launch_count() - launches0) // args.steps
     ms_step = ms_total / args.steps
-    value = C2["B"] * world / (ms_step * 1e-3)
+    value = CF["B"] * world / (ms_step * 1e-3)
 
     # ---- e2e: host batches from pinned memory, H2D on a copy stream into rotating device staging
     # buffers while the previous step computes, device-to-device into the graph's static inputs,
@@ -377,7 +426,7 @@ def main():
     loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
     loss_events = [torch.cuda.Event(), torch.cuda.Event()]
     losses = []
-    e2e_cpu = [0.0]
+    e2e_cpu, wait = [0.0], [0.0]
 
     def e2e_step(i):
         t0 = time.perf_counter()
@@ -386,23 +435,26 @@ def main():
         for t in batch.values():
             t.record_stream(torch.cuda.current_stream())
         if graphed is not None:
-            bk = graphed.stage(batch, hb["lens"])
+            bk = graphed.stage(batch, hb["lens"], tag=hb["task"])
             prefetch(i + 1)
             bk.graph.replay()
             loss = bk.loss
         else:
             prefetch(i + 1)
-            loss = eager_step(batch, hb["lens"])
+            loss = eager_step(batch, hb["lens"], hb["task"])
         # D2H read of the step's result: asynchronous copy into pinned memory, consumed while the
         # next step is already enqueued (a blocking .item() here would drain the GPU queue every
         # step, which the reference's own loop does, train_vqa.py:201 — noted, not copied)
         slot = i & 1
         loss_host[slot:slot + 1].copy_(loss.detach().float().reshape(1), non_blocking=True)
         loss_events[slot].record()
+        wait[0] = 0.0
         if i > 0:
-            loss_events[slot ^ 1].synchronize()
+            tw = time.perf_counter()
+            loss_events[slot ^ 1].synchronize()          # the host runs at most one step ahead
+            wait[0] = time.perf_counter() - tw
             losses.append(float(loss_host[slot ^ 1]))
-        e2e_cpu[0] += time.perf_counter() - t0
+        e2e_cpu[0] += time.perf_counter() - t0 - wait[0]
 
     # warm-up covers every distinct host batch once (each has its own token count: graph buckets are
     # captured / the caching allocator sees its block sizes before the timed region), and the batch
@@ -416,21 +468,21 @@ def main():
     e2e_host_ms = e2e_cpu[0] / args.steps * 1e3
     clocks = sampler.stop() if rank == 0 else None     # sampled across both timed regions (under load)
     assert all(l == l for l in losses), "NaN loss in the e2e leg"
-    e2e_value = C2["B"] * world / (ms_e2e * 1e-3)
+    e2e_value = CF["B"] * world / (ms_e2e * 1e-3)
 
-    def step(batch):                                   # eager step for the per-launch event pass
-        return eager_step(batch, lens0)
+    def step(i):                                       # eager step for the per-launch event pass
+        return eager_step(resident[i % nt], host[i % nt]["lens"], tasks[i % nt])
 
     # ---- per-kernel-role pass (CUDA events around every launch on the launching stream)
     breakdown, roofline = None, None
-    flops_step = algorithmic_flops(lens0, NL, BASE["H"])
+    flops_step = sum(algorithmic_flops(host[i]["lens"], NL, ARCH["H"]) for i in range(nt)) / nt
     pk = peaks()
     if not args.no_profile:
         NT = 24
         lib.ub200_profile_enable(1)
-        psteps = 3
+        psteps = 3 * nt
         for i in range(psteps):
-            step(resident)
+            step(i)
         ms_arr = (C.c_float * NT)()
         cnt_arr = (C.c_int * NT)()
         _lib.check(lib.ub200_profile_collect(ms_arr, cnt_arr, NT))
@@ -446,8 +498,8 @@ def main():
         gemm_ms = sum(ms_arr[i] for i in gemm_tags) / psteps
         all_ms = sum(ms_arr[i] for i in range(NT)) / psteps       # every library launch, same (serialised) mode
         gemm_launches = sum(cnt_arr[i] for i in gemm_tags) // psteps
-        T = sum(lens0)
-        gemm_flops = 3.0 * NL * 24.0 * BASE["H"] ** 2 * T          # dense-projection part of §8d
+        T = sum(sum(host[i]["lens"]) for i in range(nt)) / nt
+        gemm_flops = 3.0 * NL * 24.0 * ARCH["H"] ** 2 * T          # dense-projection part of §8d
         traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
         if os.path.exists(tp):                                      # from the committed ncu capture
@@ -481,7 +533,7 @@ def main():
                              lr=1e-6, betas=(0.9, 0.98))
 
             def opt_step(i):
-                step(resident)
+                step(i)
                 opt.step(max_grad_norm=2.0)
 
             for i in range(3):
@@ -489,35 +541,40 @@ def main():
             nst = max(5, args.steps // 2)
             ms_opt = timed(opt_step, nst) / nst
             train_step = {"ms_per_step": round(ms_opt, 4),
-                          "samples_per_s": round(C2["B"] * world / (ms_opt * 1e-3), 1),
+                          "samples_per_s": round(CF["B"] * world / (ms_opt * 1e-3), 1),
                           "includes": "fwd + bwd + global-norm clip + fused multi-tensor AdamW (fp32 masters)"}
         except Exception as e:      # informational leg: never lose the headline line over it
             train_step = {"error": "%s: %s" % (type(e).__name__, e)}
 
     # ---- CPU baseline (rank 0, N == 1 only): oracle port on the host cores, bounded sample
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == "c2":
         r = cpu_reference_run(args, 2, 1, args.cpu_sample)
         cpu = {"value": round(r["value"], 2), "unit": "samples/s", "cores": r["cores"],
                "host_cores": r["host_cores"], "kind": r["kind"], "sample": r["sample"]}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": round(value, 1), "unit": "samples/s", "n_gpus": world,
+            "metric": CF["metric"], "value": round(value, 1), "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
-            "config": {"workload": "C2: UNITER-base %d-layer encoder fwd+bwd + MLM head (15%% text masked), "
-                                   "B=64 per GPU, varlen S~54 (rank-0 batch: T=%d valid tokens, max S=%d), "
-                                   "train mode dropout 0.1" % (NL, sum(lens0), max(lens0)),
-                       "global_batch": C2["B"] * world, "parallelism": "dp%d" % world,
+            "config": {"workload": "%s: %s %d-layer encoder fwd+bwd + %s, "
+                                   "B=%d per GPU, varlen S~54 (rank-0 batch: T=%d valid tokens, max S=%d), "
+                                   "train mode dropout 0.1"
+                                   % (CF["label"], CF["arch_name"], NL,
+                                      "MLM head (15% text masked)" if tasks == ("mlm",) else
+                                      "pre-training heads, one task per step cycled " + " -> ".join(tasks) +
+                                      " (15% tokens / regions masked, 1601 region labels, OT off)",
+                                      CF["B"], sum(lens0), max(lens0)),
+                       "global_batch": CF["B"] * world, "parallelism": "dp%d" % world,
                        "l2": "per-step working set (weights 0.22 GB + saved activations ~1 GB) exceeds the "
                              "126 MB L2; no explicit flush"},
             "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "ms_per_step": round(ms_e2e, 4),
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "host_ms_per_step": round(e2e_host_ms, 3),
                     "batches": "%d distinct pinned host batches in rotation (T = %s)"
-                               % (n_host, ", ".join(str(sum(h["lens"])) for h in host))},
+                               % (n_host, ", ".join(str(sum(h["lens"])) for h in host[::nt]))},
             "step_mode": ("eager (Python enqueues every launch)" if graphed is None else
                           "cuda_graph: fwd+bwd%s replayed per token bucket of %d (%d graphs captured, "
                           "dummy-sequence padding)" % (" + gradient all-reduce" if reducer is not None else "",

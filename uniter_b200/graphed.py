@@ -67,13 +67,13 @@ class GraphedStep(object):
         self.captures = 0
 
     # ------------------------------------------------------------------ keys / buffers
-    def _key(self, host_batch, lens, accumulate):
+    def _key(self, host_batch, lens, accumulate, tag=None):
         T = int(sum(lens))
         T_pad = max(_round_up(T, self.token_bucket), self.token_bucket)
         maxseq = _round_up(max(max(lens), 1, T_pad - T), 128)
         sig = tuple((k, tuple(v.shape), str(v.dtype)) for k, v in sorted(host_batch.items())
                     if torch.is_tensor(v))
-        return (sig, T_pad, maxseq, bool(accumulate)), T_pad, maxseq
+        return (sig, T_pad, maxseq, bool(accumulate), tag), T_pad, maxseq
 
     def _fill_meta(self, bk, lens, L):
         """Packing bookkeeping of this batch -> the bucket's static device buffer (one H2D)."""
@@ -90,13 +90,13 @@ class GraphedStep(object):
         return offs
 
     # ------------------------------------------------------------------ the captured region
-    def _run(self, bk, accumulate):
+    def _run(self, bk, accumulate, tag=None):
         self.rng_counter.add_(64)                       # fresh dropout masks for this replay
         self.arena.begin_step(accumulate=accumulate, zero_all=self.zero_all)
         _model._RNG_GRAPH["dev"] = self.rng_counter
         _model._RNG_GRAPH["call"] = 0
         try:
-            loss = self.loss_fn(bk.inputs)
+            loss = self.loss_fn(bk.inputs) if tag is None else self.loss_fn(bk.inputs, tag)
             if self.reducer is not None:
                 self.reducer.backward_and_reduce(loss)
             else:
@@ -108,7 +108,7 @@ class GraphedStep(object):
             self.arena.end_step_mode()
         return loss.detach()
 
-    def _capture(self, key, host_batch, lens, T_pad, maxseq, accumulate):
+    def _capture(self, key, host_batch, lens, T_pad, maxseq, accumulate, tag=None):
         bk = _Bucket()
         bk.T_pad, bk.maxseq, bk.n_replays = T_pad, maxseq, 0
         dev = self.device
@@ -125,12 +125,22 @@ class GraphedStep(object):
         meta = _model._meta_from_buffer(bk.meta_dev, bk.meta_offs, B, L, T_pad, maxseq, None, True)
         _model._meta_store(mask, meta)            # forward() finds the static bookkeeping on this tensor
         # warm-up on a side stream (allocator, cudaFuncSetAttribute, TMA descriptor cache), then capture
+        # (the warm-up runs are REAL steps: an accumulating step would add its gradients several times
+        #  and an optimizer would move the weights, so the arena is restored and the optimizer only
+        #  prepares its device tables)
+        saved = self.arena.flat.clone() if accumulate else None
+        opt, self.optimizer = self.optimizer, None
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(self.warmup):
-                self._run(bk, accumulate)
+                self._run(bk, accumulate, tag)
+            if saved is not None:
+                self.arena.flat.copy_(saved)
         torch.cuda.current_stream().wait_stream(s)
+        self.optimizer = opt
+        if opt is not None:
+            opt.prepare()
         g = torch.cuda.CUDAGraph()
         if self.pool is None:
             self.pool = torch.cuda.graph_pool_handle()
@@ -139,7 +149,7 @@ class GraphedStep(object):
         lib.ub200_launch_count.restype = __import__("ctypes").c_ulonglong
         n0 = lib.ub200_launch_count()
         with torch.cuda.graph(g, pool=self.pool):
-            bk.loss = self._run(bk, accumulate)
+            bk.loss = self._run(bk, accumulate, tag)
         bk.launches = int(lib.ub200_launch_count() - n0)     # libub200 kernels inside one replay
         bk.graph = g
         self.buckets[key] = bk
@@ -147,13 +157,15 @@ class GraphedStep(object):
         return bk
 
     # ------------------------------------------------------------------ public
-    def stage(self, host_batch, lens, accumulate=False):
-        """Copy a host batch into its bucket's static inputs (async, current stream) and return the
-        bucket; capture the bucket's graph first if it is new."""
-        key, T_pad, maxseq = self._key(host_batch, lens, accumulate)
+    def stage(self, host_batch, lens, accumulate=False, tag=None):
+        """Copy a batch (pinned host tensors, or device tensors prefetched on a copy stream) into its
+        bucket's static inputs (async, current stream) and return the bucket; capture the bucket's
+        graph first if it is new.  `tag` (e.g. the pre-training task) becomes part of the bucket key and
+        is passed to loss_fn(batch, tag)."""
+        key, T_pad, maxseq = self._key(host_batch, lens, accumulate, tag)
         bk = self.buckets.get(key)
         if bk is None:
-            bk = self._capture(key, host_batch, lens, T_pad, maxseq, accumulate)
+            bk = self._capture(key, host_batch, lens, T_pad, maxseq, accumulate, tag)
         for k, v in host_batch.items():
             if torch.is_tensor(v):
                 bk.inputs[k].copy_(v, non_blocking=True)
@@ -161,13 +173,10 @@ class GraphedStep(object):
         self._fill_meta(bk, lens, mask.size(1))
         return bk
 
-    def stage_from_device(self, dev_batch, lens, accumulate=False):
-        """Like stage(), but the tensors already sit in device memory (e.g. prefetched on a copy
-        stream): device-to-device copies into the static inputs."""
-        return self.stage(dev_batch, lens, accumulate)
-
-    def __call__(self, batch, lens, accumulate=False):
-        bk = self.stage(batch, lens, accumulate)
+    def __call__(self, batch, lens, accumulate=False, tag=None):
+        bk = self.stage(batch, lens, accumulate, tag)
+        if self.optimizer is not None:
+            self.optimizer.sync_lr()          # the captured step reads the learning rates from the device
         bk.graph.replay()
         bk.n_replays += 1
         return bk.loss

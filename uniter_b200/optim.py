@@ -232,6 +232,14 @@ class FusedAdamW(object):
                             betas=betas, eps=eps, keep=keep)
         return self._tables
 
+    def prepare(self):
+        """Build the device tables for the current set of gradients without stepping (GraphedStep calls
+        this before capturing a step that contains the optimizer)."""
+        key = self._table_key()
+        if self._tables is None or self._tables["key"] != key:
+            self._build_tables(key)
+        self.sync_lr()
+
     def sync_lr(self):
         """Ship param_groups[*]['lr'] to the device (the training loop mutates it every step,
         train_vqa.py:207-214).  step() does this itself except inside a CUDA-graph capture: a captured
