@@ -33,6 +33,7 @@ C2 = dict(B=64, tl=(12, 28), nbb=(26, 46), seed=1234, mlm_prob=0.15)
 # BASELINE.json configs.  The default (and the driver's) run is C2, the config the
 # metric is quoted on; the others are reachable with --config for the profiles / docs.
 CONFIGS = {
+    "c5": dict(label="C5"),
     "c2": dict(label="C2", arch=BASE, arch_name="UNITER-base", metric=METRIC, tasks=("mlm",),
                B=64, tl=(12, 28), nbb=(26, 46), seed=1234, mlm_prob=0.15, mrm_prob=0.15),
     "c4": dict(label="C4", arch=LARGE, arch_name="UNITER-large",
@@ -64,7 +65,8 @@ def parse():
                     help="graph mode: token counts are padded to a multiple of this with a dummy sequence")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS),
                     help="c2 (default, the metric's config): UNITER-base MLM; c4: UNITER-large 24-layer "
-                         "pre-training step, tasks cycled mlm -> mrfr -> mrc-kl -> itm")
+                         "pre-training step, tasks cycled mlm -> mrfr -> mrc-kl -> itm; c5: UNITER-base ITM "
+                         "hard-negative iteration (400-pair no-grad scoring + 32-pair train step, both directions)")
     ap.add_argument("--layers", type=int, default=0, help=argparse.SUPPRESS)
     return ap.parse_args()
 
@@ -222,6 +224,174 @@ def cpu_reference_run(args, steps, warmup, sample_B):
                           best_n, os.cpu_count() or 1, os.cpu_count() or 1))
 
 
+# =============================================================================== C5: ITM hard negatives
+def bench_c5(args, real_out, rank, world, local_rank):
+    """BASELINE.json configs[4]: UNITER-base ITM with in-batch hard negatives
+    (train_itm_hard_negatives.py:165-199, model/itm.py:57-147).  One ITERATION = text->images
+    (1 text x 400 images: no-grad eval forward of 400 pairs, top-31 hardest, train fwd+bwd of 32
+    pairs) followed by the image->texts mirror; `train_batch_size` = 8 iterations accumulate into
+    the gradient arena before one all-reduce (config/train-itm-coco-base-16gpu-hn.json).
+    Reported: encoder sequences/s ((400 + 32) x 2 per iteration, all ranks) and the reference's
+    own counter hn_per_s (hard examples = 32 x 2 per iteration, train_itm_hard_negatives.py:230-237).
+    Eager (the hard-negative mining is data dependent: one small device->host read per direction,
+    where the reference reads too, model/itm.py:113)."""
+    import torch.distributed as dist
+    from uniter_b200 import _lib
+    from uniter_b200 import distributed as ubd
+    from uniter_b200.arena import GradArena
+    from uniter_b200.batching import hard_neg_batch_from_image, hard_neg_batch_from_text
+    from uniter_b200.heads import UniterForImageTextRetrievalHardNeg
+    from uniter_b200.model import UniterConfig, register_lengths
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    _lib.check(lib.ub200_device_check())
+    lib.ub200_launch_count.restype = C.c_ulonglong
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+    NEG, HARD, TBS, NBB, D = 399, 31, 8, 36, BASE["img_dim"]
+    torch.manual_seed(0)
+    cfg = UniterConfig(BASE["vocab"], hidden_size=BASE["H"], num_hidden_layers=args.layers or BASE["NL"],
+                       num_attention_heads=BASE["heads"], intermediate_size=BASE["I"],
+                       max_position_embeddings=BASE["max_pos"])
+    model = UniterForImageTextRetrievalHardNeg(cfg, D, margin=0.2, hard_size=HARD).to(dev, dtype).train()
+    model.init_output()
+    if world > 1:
+        ubd.broadcast_parameters(model, root=0)
+    GradArena.attach(model)
+    reducer = ubd.GradientReducer(model, overlap_chunks=1) if world > 1 else None
+
+    g = torch.Generator().manual_seed(4321 + rank)
+
+    def boxes(n):
+        xy = torch.rand(n, 4, generator=g)
+        x1 = torch.minimum(xy[:, 0], xy[:, 2]); x2 = torch.maximum(xy[:, 0], xy[:, 2])
+        y1 = torch.minimum(xy[:, 1], xy[:, 3]); y2 = torch.maximum(xy[:, 1], xy[:, 3])
+        return torch.stack([x1, y1, x2, y2, x2 - x1, y2 - y1, (x2 - x1) * (y2 - y1)], 1)
+
+    def text():
+        tl = int(torch.randint(8, 63, (1,), generator=g))
+        ids = torch.randint(1000, BASE["vocab"], (tl,), generator=g)
+        ids[0], ids[-1] = 101, 102
+        return ids
+
+    def make_iteration():
+        bt = hard_neg_batch_from_text(text(), [torch.randn(NBB, D, generator=g) for _ in range(NEG + 1)],
+                                      [boxes(NBB) for _ in range(NEG + 1)])
+        bi = hard_neg_batch_from_image(torch.randn(NBB, D, generator=g), boxes(NBB),
+                                       [text() for _ in range(NEG + 1)])
+        out = []
+        for b in (bt, bi):
+            hb = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()}
+            out.append(hb)
+        return out
+
+    n_host = 3
+    host = [make_iteration() for _ in range(n_host)]
+    h2d_bytes = sum(v.numel() * v.element_size() for it in host for hb in it for v in hb.values()
+                    if torch.is_tensor(v)) // n_host
+    seqs_per_iter = 2 * (NEG + 1 + HARD + 1)
+
+    def to_device(hb):
+        d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
+        register_lengths(d["attn_masks"], [a + b for a, b in zip(hb["txt_lens"], hb["num_bbs"])], prefix=True)
+        return d
+
+    def iteration(i, resident=None):
+        pair = resident if resident is not None else [to_device(hb) for hb in host[i % n_host]]
+        if i % TBS == 0:
+            model.zero_grad(set_to_none=True)
+        losses = []
+        for b, sf in zip(pair, ("t", "i")):
+            loss = model(dict(b), sample_from=sf, compute_loss=True).mean() / TBS
+            loss.backward()
+            losses.append(loss.detach())
+        if (i + 1) % TBS == 0 and reducer is not None:
+            reducer.reduce()
+        return losses
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    steps = max(TBS, (args.steps // TBS) * TBS)
+    resident = [to_device(hb) for hb in host[0]]
+    for i in range(max(args.warmup, 3)):
+        iteration(i, resident)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.ub200_launch_count()
+    ms_res = timed(lambda i: iteration(i, resident), steps) / steps
+    launches = (lib.ub200_launch_count() - launches0) // steps
+    for i in range(n_host):
+        iteration(i)
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def e2e_it(i):
+        ls = iteration(i)
+        if (i + 1) % TBS == 0:
+            loss_host.copy_(ls[0].float().reshape(1), non_blocking=True)
+
+    ms_e2e = timed(e2e_it, steps) / steps
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        lens_t = [a + b for a, b in zip(host[0][0]["txt_lens"], host[0][0]["num_bbs"])]
+        lens_i = [a + b for a, b in zip(host[0][1]["txt_lens"], host[0][1]["num_bbs"])]
+        NLr = args.layers or BASE["NL"]
+        f_fwd = (algorithmic_flops(lens_t, NLr, BASE["H"]) + algorithmic_flops(lens_i, NLr, BASE["H"])) / 3.0
+        f_train = 2 * 3.0 * NLr * (24.0 * BASE["H"] ** 2 * 32 * (sum(lens_t) / 400.0)
+                                   + 4.0 * BASE["H"] * 32 * (sum(lens_t) / 400.0) ** 2)
+        pk = peaks()
+        flops_iter = f_fwd + f_train
+        line = {
+            "metric": "uniter_base_itm_hardneg_encoder_sequences_per_sec",
+            "value": round(seqs_per_iter * world / (ms_res * 1e-3), 1), "unit": "sequences/s",
+            "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_res, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic",
+            "config": {"workload": "C5: UNITER-base ITM hard negatives; per iteration text->400 images and "
+                                   "image->400 texts (36 regions, text 8..62 tokens, S <= 98): no-grad eval "
+                                   "forward of 400 pairs, top-31 + positive = 32-pair train fwd+bwd each; "
+                                   "8 iterations per all-reduce; rank-0 batch T = %d / %d valid tokens"
+                                   % (sum(lens_t), sum(lens_i)),
+                       "global_batch": seqs_per_iter * world, "parallelism": "dp%d" % world},
+            "hn_per_s": round(2 * (HARD + 1) * world / (ms_res * 1e-3), 1),
+            "e2e": {"value": round(seqs_per_iter * world / (ms_e2e * 1e-3), 1), "unit": "sequences/s",
+                    "ms_per_step": round(ms_e2e, 4), "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "step_mode": "eager (data-dependent hard-negative mining)",
+            "gpu_launches": int(launches),
+            "algorithmic_tflops_per_step": round(flops_iter / 1e12, 4),
+            "achieved_tflops": round(flops_iter / (ms_res * 1e-3) / 1e12, 1),
+            "roofline": {"bound": "tensor", "kernel": "whole iteration (encoder GEMMs dominate)",
+                         "achieved": round(flops_iter / (ms_res * 1e-3) / 1e12, 1), "peak": pk["tflops"],
+                         "unit": "TFLOP/s", "frac": round(flops_iter / (ms_res * 1e-3) / 1e12 / pk["tflops"], 4),
+                         "peak_source": pk["source"], "traffic": None},
+            "clocks": clocks,
+        }
+        print(json.dumps(line), file=real_out, flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # =============================================================================== our arm
 def main():
     args = parse()
@@ -257,6 +427,8 @@ def main():
         return
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    if args.config == "c5":
+        return bench_c5(args, real_out, rank, world, local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist

@@ -171,3 +171,34 @@ def test_gemm_n_valid_over_unpadded_weight(dtype, M, V, K):
     d = (torch.randn(M, Vp, device="cuda") * 0.1).to(dtype)
     dv = d[:, :V]
     _close(ops.gemm(dv, z, a_major=1, b_major=1), dv.float().t() @ z.float(), TOL[dtype], "wgrad M = V")
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K,p_drop", [(100, 768, 768, 0.0), (3451, 768, 3072, 0.1), (517, 1024, 1024, 0.0),
+                                          (3451, 1024, 4096, 0.1), (128, 768, 64, 0.0)])
+def test_gemm_fused_residual_layernorm_epilogue(dtype, M, N, K, p_drop):
+    """UB200_EPI_LN: s = dropout(A W^T + b) + residual and LayerNorm(s) from ONE kernel (4-CTA cluster
+    over the row, statistics exchanged through distributed shared memory) against the two-kernel path
+    (bit-identical s: same accumulation order, same Philox stream) and torch's fp32 LayerNorm of that
+    s.  Rows with a large common offset check that the merged (mean, M2) statistics do not cancel."""
+    from uniter_b200 import ops
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda") * 0.5).to(dtype)
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(dtype)
+    bias = (torch.randn(N, device="cuda") * 0.1).to(dtype)
+    res = torch.randn(M, N, device="cuda")
+    res[::7] += 40.0                                   # |mean| >> std on some rows
+    res = res.to(dtype)
+    gamma = (1 + 0.1 * torch.randn(N, device="cuda")).to(dtype)
+    beta = (0.1 * torch.randn(N, device="cuda")).to(dtype)
+    kw = dict(bias=bias, residual=res, dropout_p=p_drop, rng_seed=1234, rng_stream=(7 << 20) | 3)
+    s_ref = ops.gemm(a, w, **kw)
+    s, y = ops.gemm(a, w, ln=(gamma, beta), **kw)
+    assert torch.equal(s, s_ref)
+    want = torch.nn.functional.layer_norm(s.float(), (N,), gamma.float(), beta.float(), eps=1e-12)
+    err = (y.float() - want).abs()
+    lim = (2.0 ** -9 if dtype == torch.float16 else 2.0 ** -7) * want.abs() + 1e-3     # ~1 ulp of the output
+    assert (err <= lim).all(), (err.max().item(), (err - lim).max().item())
+    y2 = ops.layernorm_fwd(s, gamma, beta)
+    assert (y.float() - y2.float()).abs().max().item() <= (2e-2 if dtype == torch.float16 else 1.3e-1)
+    assert (y != y2).float().mean().item() < 0.02      # the two paths agree up to rare last-bit ties

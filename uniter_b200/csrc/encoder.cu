@@ -1,6 +1,8 @@
 // Encoder-stack orchestration: enqueues the per-layer kernel sequence of NL BertLayers
 // (forward and backward) from C++ so that one C-ABI call covers the whole stack.
 // Reference: UniterEncoder.forward model/model.py:282-292, BertLayer model/layer.py:159-170.
+#include <stdlib.h>
+
 #include "common.h"
 
 namespace ub {
@@ -125,6 +127,11 @@ extern "C" int ub200_encoder_fwd(const ub200_encoder_desc* d, const ub200_layer_
   const ActLayout L(T, H, I, d->num_heads);
   uint8_t* act = reinterpret_cast<uint8_t*>(act_);
 
+  // residual + LayerNorm fused into the producing GEMM's epilogue where the row fits a 4-CTA cluster
+  // (H = 768 / 1024: both UNITER configs); UB200_FUSE_LN=0 selects the two-kernel path (A/B runs)
+  static const bool fuse_env = [] { const char* e = getenv("UB200_FUSE_LN"); return e && e[0] == '1'; }();
+  const bool fuse_ln = fuse_env && (H == 768 || H == 1024);
+
   const void* x = x_in;
   for (int l = 0; l < d->num_layers; ++l) {
     const ub200_layer_weights& w = layers[l];
@@ -153,19 +160,20 @@ extern "C" int ub200_encoder_fwd(const ub200_encoder_desc* d, const ub200_layer_
       UB_TRY(ub200_attn_fwd(&at, stream));
     }
 
-    // s1 = dropout(ctx Wo^T + bo) + x                          model/layer.py:112-114
+    // s1 = dropout(ctx Wo^T + bo) + x ; a = LayerNorm(s1)       model/layer.py:112-114
     g = gemm_base(d);
     g.a = A + L.ctx; g.lda = H; g.b = w.wo; g.ldb = H; g.M = T; g.N = H; g.K = H;
     g.epilogue = UB200_EPI_BIAS | UB200_EPI_RESIDUAL | (d->hidden_dropout_p > 0 ? UB200_EPI_DROPOUT : 0);
     g.bias = w.bo; g.residual = x; g.ldr = H; g.out = A + L.s1; g.ldo = H;
     g.dropout_p = d->hidden_dropout_p; g.rng_stream = rng_stream_of(d, l, SITE_ATTN_OUT);
+    if (fuse_ln) {   // LayerNorm in the GEMM epilogue (4-CTA cluster over the row)
+      g.epilogue |= UB200_EPI_LN; g.ln_gamma = w.ln1_g; g.ln_beta = w.ln1_b; g.ln_out = A + L.a; g.ldln = H;
+    }
     {
       ProfTag _t(3);
       UB_TRY(ub200_gemm(&g, stream));
     }
-
-    // a = LayerNorm(s1)                                        model/layer.py:114
-    {
+    if (!fuse_ln) {
       ProfTag _t(4);
       UB_TRY(ub200_layernorm_fwd(A + L.s1, w.ln1_g, w.ln1_b, A + L.a, T, H, d->dtype, stream));
     }
@@ -180,19 +188,20 @@ extern "C" int ub200_encoder_fwd(const ub200_encoder_desc* d, const ub200_layer_
       UB_TRY(ub200_gemm(&g, stream));
     }
 
-    // s2 = dropout(f W2^T + b2) + a                            model/layer.py:153-155
+    // s2 = dropout(f W2^T + b2) + a ; out = LayerNorm(s2)      model/layer.py:153-155
     g = gemm_base(d);
     g.a = A + L.f; g.lda = I; g.b = w.w2; g.ldb = I; g.M = T; g.N = H; g.K = I;
     g.epilogue = UB200_EPI_BIAS | UB200_EPI_RESIDUAL | (d->hidden_dropout_p > 0 ? UB200_EPI_DROPOUT : 0);
     g.bias = w.b2; g.residual = A + L.a; g.ldr = H; g.out = A + L.s2; g.ldo = H;
     g.dropout_p = d->hidden_dropout_p; g.rng_stream = rng_stream_of(d, l, SITE_FFN_OUT);
+    if (fuse_ln) {
+      g.epilogue |= UB200_EPI_LN; g.ln_gamma = w.ln2_g; g.ln_beta = w.ln2_b; g.ln_out = layer_out[l]; g.ldln = H;
+    }
     {
       ProfTag _t(6);
       UB_TRY(ub200_gemm(&g, stream));
     }
-
-    // out = LayerNorm(s2)                                      model/layer.py:155
-    {
+    if (!fuse_ln) {
       ProfTag _t(7);
       UB_TRY(ub200_layernorm_fwd(A + L.s2, w.ln2_g, w.ln2_b, layer_out[l], T, H, d->dtype, stream));
     }

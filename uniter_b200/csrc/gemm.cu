@@ -13,6 +13,8 @@ int gemm_dispatch_f16(int bn, int cluster, int a_major, int b_major, const GemmP
                       const CUtensorMap& tmA, const CUtensorMap& tmB, int grid, cudaStream_t stream);
 int gemm_group_dispatch_bf16(const void* tm, const GroupedParams& g, int grid, cudaStream_t stream);
 int gemm_group_dispatch_f16(const void* tm, const GroupedParams& g, int grid, cudaStream_t stream);
+int launch_gemm_ln(int dtype, const GemmParams& p, const void* gamma, const void* beta, void* y,
+                   long long ldy, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t stream);
 
 // Pick (N tile, CTAs per tile) minimising  waves x k-blocks x cycles-per-k-block + exposed tail.
 // Cycles per k-block are MEASURED on B200 (K = 12288 sweep, mainloop only): they are far from
@@ -69,6 +71,48 @@ extern "C" int ub200_gemm(const ub200_gemm_args* args, ub200_stream_t stream_) {
                "gemm: k_splits > 1 needs EPI_ATOMIC | EPI_OUT_F32 and a zeroed output");
   UB_CHECK_ARG(a.n_valid >= 0 && a.n_valid <= a.N, "gemm: n_valid must be in [0, N]");
   const int n_valid = a.n_valid ? a.n_valid : a.N;
+
+  if (epi & UB200_EPI_LN) {
+    // fused residual + LayerNorm epilogue: its own kernel (4-CTA cluster over N), see gemm_ln.cu
+    const int allowed = UB200_EPI_LN | UB200_EPI_BIAS | UB200_EPI_RESIDUAL | UB200_EPI_DROPOUT;
+    UB_CHECK_ARG((epi & ~allowed) == 0 && (epi & UB200_EPI_BIAS) && (epi & UB200_EPI_RESIDUAL),
+                 "gemm: EPI_LN combines with BIAS | RESIDUAL [| DROPOUT] only");
+    UB_CHECK_ARG(a.a_major == 0 && a.b_major == 0, "gemm: EPI_LN needs K-major operands");
+    UB_CHECK_ARG(a.ln_gamma && a.ln_beta && a.ln_out && a.ldln % 8 == 0, "gemm: EPI_LN needs ln_gamma / ln_beta / ln_out");
+    if (a.N != 768 && a.N != 1024)
+      return set_error(UB200_EUNSUPPORTED, "gemm: EPI_LN needs N = 768 or 1024 (got %d)", a.N);
+    const int bnl = a.N / 4;
+    CUtensorMap tmA, tmB;
+    int rc = make_tma_2d(&tmA, a.a, a.dtype, a.M, a.K, a.lda, BM, BK);
+    if (rc) return rc;
+    rc = make_tma_2d(&tmB, a.b, a.dtype, a.N, a.K, a.ldb, bnl, BK);
+    if (rc) return rc;
+    GemmParams p{};
+    p.M = a.M; p.N = a.N; p.K = a.K;
+    p.epilogue = epi;
+    p.bias = a.bias; p.residual = a.residual; p.out = a.out;
+    p.ldr = a.ldr; p.ldo = a.ldo;
+    if ((epi & UB200_EPI_DROPOUT) && a.dropout_p > 0.f) {
+      uint32_t thr = static_cast<uint32_t>(a.dropout_p * 65536.0f + 0.5f);
+      if (thr > 65535u) thr = 65535u;
+      p.drop_thr16 = thr;
+      p.drop_inv_keep = 65536.0f / static_cast<float>(65536u - thr);
+    } else {
+      p.epilogue &= ~UB200_EPI_DROPOUT;
+      p.drop_thr16 = 0;
+      p.drop_inv_keep = 1.f;
+    }
+    p.seed_lo = static_cast<uint32_t>(a.rng_seed);
+    p.seed_hi = static_cast<uint32_t>(a.rng_seed >> 32);
+    p.stream_lo = static_cast<uint32_t>(a.rng_stream);
+    p.stream_hi = static_cast<uint32_t>(a.rng_stream >> 32);
+    p.rng_dev = reinterpret_cast<const unsigned long long*>(a.rng_offset_dev);
+    p.tiles_m = (a.M + BM - 1) / BM;
+    p.tiles_n = 4;
+    p.ksplit = 1;
+    p.kb_per_split = (a.K + BK - 1) / BK;
+    return launch_gemm_ln(a.dtype, p, a.ln_gamma, a.ln_beta, a.ln_out, a.ldln, tmA, tmB, stream);
+  }
 
   const int sms = num_sms();
   int bn = 0, cluster = 0;

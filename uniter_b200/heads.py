@@ -380,18 +380,23 @@ class UniterForImageTextRetrieval(UniterPreTrainedModel):
         self.rank_output.bias.data = self.itm_output.bias.data[1:]
 
     def pooled(self, batch):
+        """pooler(sequence_output) (model/itm.py:36-42) without materialising the padded [B, L, H]
+        tensor: the [CLS] rows are gathered straight from the packed encoder output."""
         batch = defaultdict(lambda: None, batch)
-        sequence_output = self.uniter(batch["input_ids"], batch["position_ids"], batch["img_feat"],
-                                      batch["img_pos_feat"], batch["attn_masks"], batch["gather_index"],
-                                      output_all_encoded_layers=False)
-        return self.uniter.pooler(sequence_output)
+        packed, meta = self.uniter.encode_packed(
+            batch["input_ids"], batch["position_ids"], batch["img_feat"], batch["img_pos_feat"],
+            batch["attn_masks"], batch["gather_index"], output_all_encoded_layers=False)
+        B, L = meta["n_batch"], meta["L"]
+        cls_rows = meta["unpack_ext"][::L][:B].contiguous()      # packed row of position (b, 0)
+        return self.uniter.pooler(gather_packed_rows(packed, cls_rows))
 
     def itm_scores(self, batch):
         """model/pretrain.py:163-164: itm_output(pooler(sequence_output))."""
-        return self.itm_output(self.pooled(batch))
+        return LibLinear.apply(self.pooled(batch), self.itm_output.weight, self.itm_output.bias, False, False)
 
     def forward(self, batch, compute_loss=True):
-        rank_scores = self.rank_output(self.pooled(batch))
+        rank_scores = LibLinear.apply(self.pooled(batch), self.rank_output.weight, self.rank_output.bias,
+                                      False, False)
         if compute_loss:
             scores = torch.sigmoid(rank_scores).contiguous().view(-1, batch["sample_size"])
             pos, neg = scores[:, :1], scores[:, 1:]
@@ -441,8 +446,16 @@ class UniterForImageTextRetrievalHardNeg(UniterForImageTextRetrieval):
         if pos.size(0) != 1:
             pos = pos[:k + 1]
         ids, feat, box = batch["input_ids"], batch["img_feat"], batch["img_pos_feat"]
+        # host-known lengths of the candidate pairs (our collates provide them): the lengths of the
+        # mined rows are then known after ONE small read of the top-k indices, and the train forward
+        # packs without reading the device again (the reference syncs here too, model/itm.py:113)
+        lens_all = None
+        if batch["txt_lens"] is not None and batch["num_bbs"] is not None:
+            lens_all = [a + b for a, b in zip(batch["txt_lens"], batch["num_bbs"])]
+            rows_h = rows.tolist()
+            lens_sel = [lens_all[r] for r in rows_h]
         if sample_from == "t":
-            longest = masks.sum(dim=1).max().item()                         # cut to minimum padding
+            longest = max(lens_sel) if lens_all is not None else masks.sum(dim=1).max().item()   # cut to minimum padding
             n_img = longest - ids.size(1)
             masks, gather = masks[:, :longest], gather[:, :longest]
             feat = feat.index_select(0, rows)[:, :n_img, :]
@@ -453,5 +466,9 @@ class UniterForImageTextRetrievalHardNeg(UniterForImageTextRetrieval):
             feat, box = feat[:k + 1], box[:k + 1]
         else:
             raise ValueError()
+        if lens_all is not None:
+            from .model import register_lengths
+            masks = masks.contiguous()
+            register_lengths(masks, lens_sel, prefix=True)
         return {"sample_size": k + 1, "input_ids": ids, "position_ids": pos, "img_feat": feat,
                 "img_pos_feat": box, "attn_masks": masks, "gather_index": gather}
