@@ -61,6 +61,8 @@ def parse():
                     help="N>1: SMs left to the overlapped all-reduce (and its CTA cap)")
     ap.add_argument("--no-graph", action="store_true",
                     help="enqueue every step from Python (eager) instead of replaying CUDA graphs")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "in-graph", "after"],
+                    help="N>1 graph mode: capture the NCCL all-reduces inside the graph (auto: try, else after)")
     ap.add_argument("--token-bucket", type=int, default=128,
                     help="graph mode: token counts are padded to a multiple of this with a dummy sequence")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS),
@@ -511,8 +513,31 @@ def main():
             return model(batch, "itm")[0].mean()
         raise ValueError(task)
 
-    graphed = None if args.no_graph else GraphedStep(model, loss_fn, token_bucket=args.token_bucket,
-                                                     reducer=reducer)
+    # N > 1: the gradient all-reduces are captured INSIDE the graph (overlapped with the backward on a
+    # side stream, exactly like the eager reducer); --allreduce after keeps them out of the graph and
+    # issues them after each replay (fallback; chosen automatically if the in-graph capture fails)
+    ar_mode = "none" if reducer is None else args.allreduce
+    graphed = None
+    if not args.no_graph:
+        graphed = GraphedStep(model, loss_fn, token_bucket=args.token_bucket,
+                              reducer=reducer if ar_mode in ("in-graph", "auto") else None)
+        if ar_mode == "auto":
+            ar_mode = "in-graph"
+            try:       # probe: capture + one replay of the first batch's bucket with NCCL inside
+                pb = {k: v for k, v in host[0].items() if torch.is_tensor(v)}
+                bk = graphed.stage(pb, host[0]["lens"], tag=host[0]["task"])
+                bk.graph.replay()
+                torch.cuda.synchronize()
+            except Exception as e:      # noqa: BLE001  (symmetric across ranks: same code, same NCCL)
+                sys.stderr.write("in-graph all-reduce unavailable (%s: %s); reducing after each replay\n"
+                                 % (type(e).__name__, e))
+                ar_mode = "after"
+                graphed = GraphedStep(model, loss_fn, token_bucket=args.token_bucket, reducer=None)
+
+    def replay(bk):
+        bk.graph.replay()
+        if ar_mode == "after":
+            reducer.reduce()
 
     def to_device(hb, stream):
         with torch.cuda.stream(stream):
@@ -557,8 +582,8 @@ def main():
     if graphed is not None:
         bks = [graphed.stage(resident[i], host[i]["lens"], tag=tasks[i]) for i in range(nt)]   # captures (untimed)
         for i in range(args.warmup):
-            bks[i % nt].graph.replay()
-        step_resident = lambda i: bks[i % nt].graph.replay()  # noqa: E731
+            replay(bks[i % nt])
+        step_resident = lambda i: replay(bks[i % nt])  # noqa: E731
     else:
         for i in range(args.warmup):
             eager_step(resident[i % nt], host[i % nt]["lens"], tasks[i % nt])
@@ -609,7 +634,7 @@ def main():
         if graphed is not None:
             bk = graphed.stage(batch, hb["lens"], tag=hb["task"])
             prefetch(i + 1)
-            bk.graph.replay()
+            replay(bk)
             loss = bk.loss
         else:
             prefetch(i + 1)
@@ -749,7 +774,8 @@ def main():
                                % (n_host, ", ".join(str(sum(h["lens"])) for h in host[::nt]))},
             "step_mode": ("eager (Python enqueues every launch)" if graphed is None else
                           "cuda_graph: fwd+bwd%s replayed per token bucket of %d (%d graphs captured, "
-                          "dummy-sequence padding)" % (" + gradient all-reduce" if reducer is not None else "",
+                          "dummy-sequence padding)" % (" + gradient all-reduce" if ar_mode == "in-graph" else
+                                                       (", all-reduce after each replay" if ar_mode == "after" else ""),
                                                        args.token_bucket, graphed.captures)),
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(cpu_enqueue_ms, 3),
             "algorithmic_tflops_per_step": round(flops_step / 1e12, 4),

@@ -78,7 +78,8 @@ class GradientReducer:
         self.overlap_chunks = overlap_chunks
         self._pending = []
         self._done = []               # element ranges of the arena already shipped in this step
-        self._comm_stream = None
+        # created up front: the first use may be inside a CUDA-graph capture
+        self._comm_stream = torch.cuda.Stream() if self.arena.flat.is_cuda else None
         self._reserved = False
         self._bwd_seen = {}
 
