@@ -213,6 +213,9 @@ typedef struct {
   int32_t dropout_on_dy;    /* bit 0: y = dropout(LN(x)) (embeddings): mask dy instead of emitting dx_drop;
                                bit 1: with row_kind, rows of the OTHER kind get dx = 0 (else untouched) */
   const uint64_t* rng_offset_dev; /* optional device counter added to rng_stream (see ub200_gemm_args) */
+  float* stats_ws;          /* optional scratch, rows x 2 floats: selects the split form (a row kernel that
+                               carries nothing between rows + a column-reduction kernel) for the plain
+                               case (no row_kind, dropout on the Linear branch); NULL = one fused kernel */
 } ub200_ln_bwd_args;
 int ub200_layernorm_bwd(const ub200_ln_bwd_args* args, ub200_stream_t stream);
 

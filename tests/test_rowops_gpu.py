@@ -5,9 +5,10 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("split", [False, True])
 @pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 2e-2), (torch.float16, 3e-3)])
 @pytest.mark.parametrize("rows,H", [(1, 768), (3451, 768), (517, 1024), (33, 128)])
-def test_layernorm_fwd_bwd(dtype, tol, rows, H):
+def test_layernorm_fwd_bwd(dtype, tol, rows, H, split):
     from uniter_b200 import ops
     torch.manual_seed(rows + H)
     x = (torch.randn(rows, H, device="cuda") * 2 + 0.3).to(dtype)
@@ -21,7 +22,7 @@ def test_layernorm_fwd_bwd(dtype, tol, rows, H):
     ref.backward(dy.float())
     y = ops.layernorm_fwd(x, g, b)
     assert (y.float() - ref).abs().max().item() <= tol * max(1, ref.abs().max().item())
-    dx, dxd, dg, db, dbias = ops.layernorm_bwd(dy, x, g)
+    dx, dxd, dg, db, dbias = ops.layernorm_bwd(dy, x, g, split=split)   # split: row + column kernels
     assert dxd is None
     assert (dx.float() - x32.grad).abs().max().item() <= tol * max(1, x32.grad.abs().max().item())
     assert (dg - g32.grad).abs().max().item() <= 2e-3 * max(1, g32.grad.abs().max().item())
@@ -30,7 +31,8 @@ def test_layernorm_fwd_bwd(dtype, tol, rows, H):
     assert (dbias - dx.float().sum(0)).abs().max().item() <= 1e-3 * max(1, dbias.abs().max().item())
 
 
-def test_layernorm_bwd_dropout_mask_matches_gemm_epilogue():
+@pytest.mark.parametrize("split", [False, True])
+def test_layernorm_bwd_dropout_mask_matches_gemm_epilogue(split):
     """The backward must regenerate exactly the mask the forward GEMM epilogue applied."""
     from uniter_b200 import ops
     torch.manual_seed(0)
@@ -41,7 +43,7 @@ def test_layernorm_bwd_dropout_mask_matches_gemm_epilogue():
     mask = fwd != 0
     dy = torch.randn(rows, H, device="cuda").bfloat16()
     g = torch.ones(H, device="cuda").bfloat16()
-    dx, dxd, _, _, dbias = ops.layernorm_bwd(dy, x, g, dropout_p=0.1, rng_seed=77, rng_stream=9)
+    dx, dxd, _, _, dbias = ops.layernorm_bwd(dy, x, g, dropout_p=0.1, rng_seed=77, rng_stream=9, split=split)
     nz = x != 0
     assert torch.equal((dxd != 0) | ~nz | (dx == 0), mask | ~nz | (dx == 0))
     kept = dxd != 0

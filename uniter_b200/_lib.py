@@ -54,7 +54,7 @@ class LnBwdArgs(C.Structure):
         ("rows", C.c_int32), ("hidden", C.c_int32), ("dtype", C.c_int32),
         ("dropout_p", C.c_float), ("rng_seed", C.c_uint64), ("rng_stream", C.c_uint64),
         ("row_kind", C.c_void_p), ("kind", C.c_int32), ("dropout_on_dy", C.c_int32),
-        ("rng_offset_dev", C.c_void_p),
+        ("rng_offset_dev", C.c_void_p), ("stats_ws", C.c_void_p),
     ]
 
 

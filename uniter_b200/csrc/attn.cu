@@ -82,8 +82,14 @@ __device__ __forceinline__ void st_swz128(uint8_t* base, int r, int col8, uint4 
   *reinterpret_cast<uint4*>(p) = v;
 }
 
-template <bool kBF16>
-__global__ void __launch_bounds__(128)
+// kSingle: every sequence of the launch fits one 128-key block (max_seqlen <= 128: all of C2 / C4 / C5).
+// The kernel is latency bound (TMA -> MMA -> TMEM -> exp -> smem -> MMA -> TMEM -> store, one chain
+// per CTA), so what matters is how many CTAs an SM can hold.  With one key block Q and K are dead
+// once S = Q K^T has completed and S is dead once P has been extracted, so P overwrites the Q|K
+// tiles and O overwrites the S columns: 48 KB smem + 128 TMEM columns per CTA -> 4 CTAs / SM
+// instead of 2 (80 KB, 256 columns).
+template <bool kBF16, bool kSingle>
+__global__ void __launch_bounds__(128, kSingle ? 4 : 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmQKV64,
                 const AttnParams p) {
   pdl_launch_dependents();
@@ -103,13 +109,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint32_t rs0 = p.stream_lo, rs1 = p.stream_hi;
   if (p.drop_thr16) rng_add_dev_offset(p.rng_dev, rs0, rs1);
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // kSingle requests no alignment slack (4 CTAs must fit an SM): the dynamic window starts 1024-aligned
+  uint8_t* smem = smem_raw + (kSingle ? 0u : ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  if (kSingle && (smem_u32(smem_raw) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;
   uint8_t* sK = smem + ATT_TILE;
   uint8_t* sV = smem + 2 * ATT_TILE;
-  uint8_t* sP = smem + 3 * ATT_TILE;  // 2 slabs
-  uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + 5 * ATT_TILE);
+  uint8_t* sP = kSingle ? smem : smem + 3 * ATT_TILE;  // 2 slabs (kSingle: over the dead Q | K tiles)
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + (kSingle ? 3 : 5) * ATT_TILE);
   uint64_t* bar_mma = bar_load + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
 
@@ -122,15 +130,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, kSingle ? 128 : 256);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem;          // 128 fp32 columns
-  const uint32_t tO = tmem + 128;    // 64 fp32 columns
+  const uint32_t tS = tmem;                        // 128 fp32 columns
+  const uint32_t tO = kSingle ? tmem : tmem + 128;   // 64 fp32 columns (kSingle: over the dead S columns)
   const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
 
   // this thread's query row: (head, position in the sequence, first key column of its block)
@@ -311,11 +319,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 256);
+    tmem_dealloc(tmem, kSingle ? 128 : 256);
   }
 }
 
 constexpr int ATT_FWD_SMEM = 5 * ATT_TILE + 64 + 1024;
+constexpr int ATT_FWD_SMEM_SINGLE = 3 * ATT_TILE + 64;
 
 // =====================================================================================
 // Backward.  One CTA per (128-key block j, head, sequence); loops over 128-query blocks i.
@@ -325,8 +334,12 @@ constexpr int ATT_FWD_SMEM = 5 * ATT_TILE + 64 + 1024;
 //   (dV = Pd^T dO, dK = dS^T Q) by tcgen05.
 // dQ of a sequence longer than one key block is accumulated with fp32 atomics in `dq_accum`.
 // =====================================================================================
-template <bool kBF16>
-__global__ void __launch_bounds__(256)
+// kSingle (max_seqlen <= 128, one query block and one key block per sequence): V is dead after
+// dP = dO V^T and S / dP are dead once P / dS have been extracted, so the first P slab overwrites the
+// V tile and dV | dK | dQ overwrite the S | dP columns: 112 KB smem + 256 TMEM columns -> 2 CTAs / SM
+// (128 registers x 256 threads x 2 = the whole register file) instead of 1.
+template <bool kBF16, bool kSingle>
+__global__ void __launch_bounds__(256, kSingle ? 2 : 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmQKV64, const __grid_constant__ CUtensorMap tmDO64,
                 const AttnParams p, float* dq_accum) {
@@ -349,15 +362,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int kv_len = pair ? S : min(ATT_BN, S - j * ATT_BN);
   const int n_pad = pair ? ATT_BN : ((kv_len + 15) & ~15);
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + (kSingle ? 0u : ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  if (kSingle && (smem_u32(smem_raw) & 1023u) != 0) __trap();
   uint8_t* sQ = smem;
   uint8_t* sdO = smem + ATT_TILE;
   uint8_t* sK = smem + 2 * ATT_TILE;
   uint8_t* sV = smem + 3 * ATT_TILE;
-  uint8_t* sP = smem + 4 * ATT_TILE;   // 2 slabs
-  uint8_t* sDS = smem + 6 * ATT_TILE;  // 2 slabs
-  uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + 8 * ATT_TILE);
+  uint8_t* sP = smem + (kSingle ? 3 : 4) * ATT_TILE;   // 2 slabs (kSingle: slab 0 over the dead V tile)
+  uint8_t* sDS = smem + (kSingle ? 5 : 6) * ATT_TILE;  // 2 slabs
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(smem + (kSingle ? 7 : 8) * ATT_TILE);
   uint64_t* bar_mma = bar_load + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
 
@@ -377,14 +391,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, kSingle ? 256 : 512);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
+  const uint32_t tS = tmem, tP = tmem + 128;
+  const uint32_t tdV = tmem + (kSingle ? 0 : 256), tdK = tmem + (kSingle ? 64 : 320),
+                 tdQ = tmem + (kSingle ? 128 : 384);
   const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const int bh = b * p.nheads + head;
   const float c = p.scale * 1.4426950408889634f;
@@ -605,7 +621,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, kSingle ? 256 : 512);
   }
 }
 
@@ -634,6 +650,7 @@ __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, void* dqkv
 }
 
 constexpr int ATT_BWD_SMEM = 8 * ATT_TILE + 64 + 1024;
+constexpr int ATT_BWD_SMEM_SINGLE = 7 * ATT_TILE + 64;
 
 }  // namespace ub
 
@@ -677,23 +694,24 @@ extern "C" int ub200_attn_fwd(const ub200_attn_args* args, ub200_stream_t stream
   p.rng_dev = reinterpret_cast<const unsigned long long*>(a.rng_offset_dev);
 
   dim3 grid((a.max_seqlen + ATT_BM - 1) / ATT_BM, a.num_heads, a.batch);
-  static bool configured[2] = {false, false};
-  if (a.dtype == UB200_BF16) {
-    if (!configured[1]) {
-      UB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
-      configured[1] = true;
-    }
+  const bool single = a.max_seqlen <= ATT_BN;
+  const bool bf = a.dtype == UB200_BF16;
+  void (*kern)(const CUtensorMap, const CUtensorMap, const AttnParams) =
+      single ? (bf ? attn_fwd_kernel<true, true> : attn_fwd_kernel<false, true>)
+             : (bf ? attn_fwd_kernel<true, false> : attn_fwd_kernel<false, false>);
+  const int smem_bytes = single ? ATT_FWD_SMEM_SINGLE : ATT_FWD_SMEM;
+  static bool configured[4] = {false, false, false, false};
+  const int ci = (single ? 2 : 0) + (bf ? 1 : 0);
+  if (!configured[ci]) {
+    UB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    if (single)   // 4 CTAs x 49 KB per SM: ask for the full shared-memory carve-out
+      UB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
+    configured[ci] = true;
+  }
+  {
     ProfScope ps(stream);
-    UB_CHECK_CUDA(launch_pdl(attn_fwd_kernel<true>, grid, dim3(128), ATT_FWD_SMEM, stream, 1, tm, tm64, p));
-  } else {
-    if (!configured[0]) {
-      UB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM));
-      configured[0] = true;
-    }
-    ProfScope ps(stream);
-    UB_CHECK_CUDA(launch_pdl(attn_fwd_kernel<false>, grid, dim3(128), ATT_FWD_SMEM, stream, 1, tm, tm64, p));
+    UB_CHECK_CUDA(launch_pdl(kern, grid, dim3(128), smem_bytes, stream, 1, tm, tm64, p));
   }
   UB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -752,19 +770,25 @@ extern "C" int ub200_attn_bwd(const ub200_attn_args* args, ub200_stream_t stream
     UB_CHECK_CUDA(cudaMemsetAsync(acc, 0, static_cast<size_t>(a.total_tokens) * a.hidden * 4, stream));
 
   dim3 grid((a.max_seqlen + ATT_BN - 1) / ATT_BN, a.num_heads, a.batch);
-  static bool configured[2] = {false, false};
+  const bool single = !multi;
   const int di = a.dtype == UB200_BF16 ? 1 : 0;
-  if (!configured[di]) {
-    if (di) UB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
-    else UB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BWD_SMEM));
-    configured[di] = true;
+  void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams,
+               float*) =
+      single ? (di ? attn_bwd_kernel<true, true> : attn_bwd_kernel<false, true>)
+             : (di ? attn_bwd_kernel<true, false> : attn_bwd_kernel<false, false>);
+  const int smem_bytes = single ? ATT_BWD_SMEM_SINGLE : ATT_BWD_SMEM;
+  static bool configured[4] = {false, false, false, false};
+  const int ci = (single ? 2 : 0) + di;
+  if (!configured[ci]) {
+    UB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    if (single)
+      UB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
+    configured[ci] = true;
   }
   {
     ProfScope ps(stream);
-    if (di) UB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true>, grid, dim3(256), ATT_BWD_SMEM, stream, 1, tmQ, tmD, tmQ64, tmD64, p, acc));
-    else UB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false>, grid, dim3(256), ATT_BWD_SMEM, stream, 1, tmQ, tmD, tmQ64, tmD64, p, acc));
+    UB_CHECK_CUDA(launch_pdl(kern, grid, dim3(256), smem_bytes, stream, 1, tmQ, tmD, tmQ64, tmD64, p, acc));
   }
   UB_CHECK_CUDA(cudaGetLastError());
   if (multi) {

@@ -27,7 +27,7 @@ struct ActLayout {
 };
 
 struct BwdScratch {
-  int64_t bufA, bufB, bufC, bufD, bufE, g0, g1, dpre, dqkv, attn_ws, total;
+  int64_t bufA, bufB, bufC, bufD, bufE, g0, g1, dpre, dqkv, attn_ws, ln_stats, total;
   BwdScratch(int64_t T, int64_t H, int64_t I, int64_t attn_ws_bytes) {
     int64_t o = 0;
     bufA = o; o += align256(T * H * 2);   // ds2
@@ -40,6 +40,7 @@ struct BwdScratch {
     dpre = o; o += align256(T * I * 2);
     dqkv = o; o += align256(T * 3 * H * 2);
     attn_ws = o; o += align256(attn_ws_bytes);
+    ln_stats = o; o += align256(T * 2 * 4);   // (mean, rstd) per row for the split LayerNorm backward
     total = o;
   }
 };
@@ -235,6 +236,9 @@ extern "C" int ub200_encoder_bwd(const ub200_encoder_desc* d, const ub200_layer_
   cudaStream_t cs = reinterpret_cast<cudaStream_t>(stream);
   const bool drop = d->hidden_dropout_p > 0.f;
   const int acc = accumulate_wgrad ? UB200_EPI_ACCUM : 0;
+  // UB200_LN_BWD_SPLIT=1: row kernel + column kernel instead of the fused LayerNorm backward (A/B runs)
+  static const bool ln_split = [] { const char* e = getenv("UB200_LN_BWD_SPLIT"); return e && e[0] == '1'; }();
+  float* ln_ws = ln_split ? reinterpret_cast<float*>(sc + S.ln_stats) : nullptr;
 
   const void* dcur = d_layer_out[NL - 1];
   int pp = 0;  // ping-pong for the running gradient
@@ -254,7 +258,7 @@ extern "C" int ub200_encoder_bwd(const ub200_encoder_desc* d, const ub200_layer_
     ln.dgamma = gr.small + SG.dg2; ln.dbeta = gr.small + SG.db2ln; ln.dbias = gr.small + SG.db2;
     ln.rows = T; ln.hidden = H; ln.dtype = d->dtype; ln.dropout_p = d->hidden_dropout_p;
     ln.rng_seed = d->rng_seed; ln.rng_stream = rng_stream_of(d, l, SITE_FFN_OUT);
-    ln.rng_offset_dev = d->rng_offset_dev;
+    ln.rng_offset_dev = d->rng_offset_dev; ln.stats_ws = ln_ws;
     {
       ProfTag _t(8);
       UB_TRY(ub200_layernorm_bwd(&ln, stream));
@@ -286,7 +290,7 @@ extern "C" int ub200_encoder_bwd(const ub200_encoder_desc* d, const ub200_layer_
     ln.dgamma = gr.small + SG.dg1; ln.dbeta = gr.small + SG.db1ln; ln.dbias = gr.small + SG.dbo;
     ln.rows = T; ln.hidden = H; ln.dtype = d->dtype; ln.dropout_p = d->hidden_dropout_p;
     ln.rng_seed = d->rng_seed; ln.rng_stream = rng_stream_of(d, l, SITE_ATTN_OUT);
-    ln.rng_offset_dev = d->rng_offset_dev;
+    ln.rng_offset_dev = d->rng_offset_dev; ln.stats_ws = ln_ws;
     {
       ProfTag _t(13);
       UB_TRY(ub200_layernorm_bwd(&ln, stream));

@@ -290,6 +290,154 @@ ln_bwd_kernel(const LnBwdParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------ LayerNorm bwd, split form
+// The fused kernel above keeps 3 x NV x 8 column accumulators per thread (240 registers at H = 768:
+// one CTA of 8 warps per SM) and every warp walks through a serial chain of 3 warp reductions per
+// row, so it runs at ~0.2 of the HBM roofline (ncu: 15 us for 21 MB).  Split form, for the plain case
+// (no row-kind mask, dropout on the Linear branch):
+//   ln_bwd_rows_kernel  one warp per row, nothing carried between rows (~90 registers: several CTAs
+//                       per SM): dx, the dropout-masked copy, and (mean, rstd) of the row to `stats`;
+//   ln_bwd_cols_kernel  dgamma / dbeta / dbias as column reductions over a [64 columns x row slab]
+//                       block per CTA (the operands are L2-hot), 12x fewer atomics per address.
+template <bool kBF16, int NV>
+__global__ void __launch_bounds__(256, 2)
+ln_bwd_rows_kernel(const LnBwdParams p, float2* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
+  using T16 = typename Elem<kBF16>::T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= p.rows) return;
+  const int H = p.H, nvec = H >> 3;
+  const float inv_h = 1.0f / H;
+  float xv[NV][8], dv[NV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(p.x) +
+                                                          static_cast<size_t>(row) * H) + vi), xv[i]);
+      unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(p.dy) +
+                                                          static_cast<size_t>(row) * H) + vi), dv[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += xv[i][e];
+    }
+  }
+  const float mean = warp_sum(sum) * inv_h;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (lane + i * 32 < nvec) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = xv[i][e] - mean; sq += d * d; }
+    }
+  const float rstd = rsqrtf(warp_sum(sq) * inv_h + LN_EPS);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      float gam[8];
+      unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(p.gamma) + vi), gam);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xh = (xv[i][e] - mean) * rstd;
+        const float g = dv[i][e] * gam[e];
+        s1 += g; s2 += g * xh;
+        xv[i][e] = xh;
+        dv[i][e] = g;
+      }
+    }
+  }
+  s1 = warp_sum(s1) * inv_h;
+  s2 = warp_sum(s2) * inv_h;
+  if (lane == 0) stats[row] = make_float2(mean, rstd);
+  DropoutRng rng;
+  rng.k0 = p.seed_lo; rng.k1 = p.seed_hi; rng.s0 = p.stream_lo; rng.s1 = p.stream_hi;
+  if (p.drop_thr16) rng_add_dev_offset(p.rng_dev, rng.s0, rng.s1);
+  rng.thr16 = p.drop_thr16; rng.inv_keep = p.drop_inv_keep;
+  uint4* dxr = reinterpret_cast<uint4*>(reinterpret_cast<T16*>(p.dx) + static_cast<size_t>(row) * H);
+  uint4* ddr = p.dx_drop ? reinterpret_cast<uint4*>(reinterpret_cast<T16*>(p.dx_drop) + static_cast<size_t>(row) * H)
+                         : nullptr;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = rstd * (dv[i][e] - s1 - xv[i][e] * s2);
+      dxr[vi] = pack8<kBF16>(o);
+      if (ddr) {
+        const uint64_t el = static_cast<uint64_t>(row) * H + vi * 8;
+        const uint4 rnd = rng.draw8(el >> 3);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (rand16_of(rnd, e) < rng.thr16) ? 0.f : o[e] * rng.inv_keep;
+        ddr[vi] = pack8<kBF16>(o);
+      }
+    }
+  }
+}
+
+// CTA = 8 column vectors (64 columns) x 32 row lanes over rows [r0, r1).
+template <bool kBF16>
+__global__ void __launch_bounds__(256)
+ln_bwd_cols_kernel(const LnBwdParams p, const float2* __restrict__ stats, int rows_per_cta) {
+  pdl_launch_dependents();
+  pdl_wait();
+  using T16 = typename Elem<kBF16>::T;
+  __shared__ float red[3][32][64 + 1];
+  const int cv = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int col0 = (blockIdx.x * 8 + cv) * 8;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(p.rows, r0 + rows_per_cta);
+  const int H = p.H;
+  const void* lin = p.dx_drop ? p.dx_drop : p.dx;      // what the Linear branch receives
+  float ag[8], ab[8], ad[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { ag[e] = 0.f; ab[e] = 0.f; ad[e] = 0.f; }
+  if (col0 < H) {
+    for (int r = r0 + rl; r < r1; r += 32) {
+      const float2 st = __ldg(stats + r);
+      float x[8], dy[8];
+      unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(p.x) +
+                                                          static_cast<size_t>(r) * H + col0)), x);
+      unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(p.dy) +
+                                                          static_cast<size_t>(r) * H + col0)), dy);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        ag[e] = fmaf(dy[e], (x[e] - st.x) * st.y, ag[e]);
+        ab[e] += dy[e];
+      }
+      if (p.dbias) {
+        float d[8];
+        unpack8<kBF16>(*reinterpret_cast<const uint4*>(reinterpret_cast<const T16*>(lin) +
+                                                       static_cast<size_t>(r) * H + col0), d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ad[e] += d[e];
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    red[0][rl][cv * 8 + e] = ag[e];
+    red[1][rl][cv * 8 + e] = ab[e];
+    red[2][rl][cv * 8 + e] = ad[e];
+  }
+  __syncthreads();
+  if (threadIdx.x < 192) {
+    const int q = threadIdx.x >> 6, c = threadIdx.x & 63;
+    const int col = blockIdx.x * 64 + c;
+    if (col < H && (q < 2 || p.dbias)) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 32; ++w) s += red[q][w][c];
+      float* dst = q == 0 ? p.dgamma : (q == 1 ? p.dbeta : p.dbias);
+      atomicAdd(dst + col, s);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ gather rows
 template <int kDummy>
 __global__ void __launch_bounds__(256)
@@ -414,6 +562,42 @@ static cudaError_t launch_ln_bwd_nv(const LnBwdParams& p, int grid, cudaStream_t
   }
 }
 
+template <bool kBF16>
+static cudaError_t launch_ln_bwd_rows_nv(const LnBwdParams& p, float2* stats, int grid, cudaStream_t stream) {
+  const int nv = (p.H + 255) / 256;
+  switch (nv) {
+    case 1: return launch_pdl(ln_bwd_rows_kernel<kBF16, 1>, dim3(grid), dim3(256), 0, stream, 1, p, stats);
+    case 2: return launch_pdl(ln_bwd_rows_kernel<kBF16, 2>, dim3(grid), dim3(256), 0, stream, 1, p, stats);
+    case 3: return launch_pdl(ln_bwd_rows_kernel<kBF16, 3>, dim3(grid), dim3(256), 0, stream, 1, p, stats);
+    default: return launch_pdl(ln_bwd_rows_kernel<kBF16, 4>, dim3(grid), dim3(256), 0, stream, 1, p, stats);
+  }
+}
+
+// split form (see ln_bwd_rows_kernel): needs `stats` = rows x 2 floats of caller-owned scratch
+int launch_ln_bwd_split(int dtype, const LnBwdParams& p, float* stats_ws, cudaStream_t stream) {
+  float2* stats = reinterpret_cast<float2*>(stats_ws);
+  const bool bf = dtype == UB200_BF16;
+  {
+    ProfScope ps(stream);
+    const int grid = (p.rows + 7) / 8;
+    if (bf) UB_CHECK_CUDA(launch_ln_bwd_rows_nv<true>(p, stats, grid, stream));
+    else UB_CHECK_CUDA(launch_ln_bwd_rows_nv<false>(p, stats, grid, stream));
+  }
+  {
+    const int gx = (p.H + 63) / 64;
+    int gy = (2 * num_sms() + gx - 1) / gx;
+    if (gy > (p.rows + 31) / 32) gy = (p.rows + 31) / 32;
+    if (gy < 1) gy = 1;
+    const int rpc = (p.rows + gy - 1) / gy;
+    ProfScope ps(stream);
+    if (bf) UB_CHECK_CUDA(launch_pdl(ln_bwd_cols_kernel<true>, dim3(gx, gy), dim3(256), 0, stream, 1, p,
+                                     static_cast<const float2*>(stats), rpc));
+    else UB_CHECK_CUDA(launch_pdl(ln_bwd_cols_kernel<false>, dim3(gx, gy), dim3(256), 0, stream, 1, p,
+                                  static_cast<const float2*>(stats), rpc));
+  }
+  return 0;
+}
+
 int launch_ln_bwd(int dtype, const LnBwdParams& p, cudaStream_t stream) {
   if (p.H % 8 != 0 || p.H > LN_MAX_VEC * 256 || p.rows <= 0)
     return set_error(UB200_EUNSUPPORTED, "ln_bwd: need rows > 0, H %% 8 == 0 and H <= %d (H=%d)",
@@ -531,6 +715,13 @@ extern "C" int ub200_layernorm_bwd(const ub200_ln_bwd_args* a, ub200_stream_t st
   p.stream_lo = static_cast<uint32_t>(a->rng_stream);
   p.stream_hi = static_cast<uint32_t>(a->rng_stream >> 32);
   p.rng_dev = reinterpret_cast<const unsigned long long*>(a->rng_offset_dev);
+  if (a->stats_ws != nullptr && a->row_kind == nullptr && !p.dy_drop) {
+    UB_CHECK_ARG((reinterpret_cast<uintptr_t>(a->stats_ws) & 7) == 0, "layernorm_bwd: stats_ws must be 8-byte aligned");
+    if (p.H % 8 != 0 || p.H > ub::LN_MAX_VEC * 256 || p.rows <= 0)
+      return ub::set_error(UB200_EUNSUPPORTED, "ln_bwd: need rows > 0, H %% 8 == 0 and H <= %d (H=%d)",
+                           ub::LN_MAX_VEC * 256, p.H);
+    return ub::launch_ln_bwd_split(a->dtype, p, a->stats_ws, reinterpret_cast<cudaStream_t>(stream));
+  }
   return ub::launch_ln_bwd(a->dtype, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
