@@ -249,16 +249,10 @@ def _front(model, b, gi, training=False):
     """Packed embedding rows through the fused front-end (internal entry used by forward())."""
     from uniter_b200.model import _EmbedFront
     meta = model._pack_meta(b["attn_masks"])
-    te, ie = model.embeddings, model.img_embeddings
     model._weight_table()
-    x = _EmbedFront.apply(
-        model, meta, 0, b["input_ids"], b["position_ids"], b["img_feat"], b["img_pos_feat"], gi,
-        None, None, None, 0.0,
-        te.word_embeddings.weight, te.position_embeddings.weight, te.token_type_embeddings.weight,
-        te.LayerNorm.weight, te.LayerNorm.bias, ie.img_linear.weight, ie.img_linear.bias,
-        ie.img_layer_norm.weight, ie.img_layer_norm.bias, ie.pos_layer_norm.weight,
-        ie.pos_layer_norm.bias, ie.pos_linear.weight, ie.pos_linear.bias,
-        ie.mask_embedding.weight, ie.LayerNorm.weight, ie.LayerNorm.bias)
+    anchor = torch.zeros(1, device="cuda", requires_grad=True)
+    x = _EmbedFront.apply(anchor, model, meta, 0, b["input_ids"], b["position_ids"], b["img_feat"],
+                          b["img_pos_feat"], gi, None, None, None, 0.0)
     return x, meta
 
 
