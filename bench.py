@@ -497,8 +497,16 @@ def main():
     host = []
     for i in range(n_host):
         task = tasks[i % len(tasks)]
-        b = synth_batch(CF["B"], CF["tl"][0], CF["tl"][1], CF["nbb"][0], CF["nbb"][1],
-                        CF["seed"] + 1000 * rank + (i // len(tasks)), mlm_prob=CF["mlm_prob"])
+        if i < len(tasks):
+            # the canonical batch of the config (seed 1234 -> T = 3451 on rank 0)
+            b = synth_batch(CF["B"], CF["tl"][0], CF["tl"][1], CF["nbb"][0], CF["nbb"][1],
+                            CF["seed"] + 1000 * rank, mlm_prob=CF["mlm_prob"])
+            canon = (b["txt_lens"], b["num_bbs"])
+        else:
+            # further host batches of the rotation: the SAME length profile (so that the e2e leg does
+            # the same work per step as the resident leg) with different token ids / features / masks
+            b = synth_batch(CF["B"], 0, 0, 0, 0, CF["seed"] + 1000 * rank + 7 * (i // len(tasks)),
+                            txt_lens=canon[0], num_bbs=canon[1], mlm_prob=CF["mlm_prob"])
         lens = [a + c for a, c in zip(b["txt_lens"], b["num_bbs"])]
         if task == "mlm":
             b = pad_mlm_index(b, 64)
@@ -790,8 +798,9 @@ def main():
             "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "ms_per_step": round(ms_e2e, 4),
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "host_ms_per_step": round(e2e_host_ms, 3),
-                    "batches": "%d distinct pinned host batches in rotation (T = %s)"
-                               % (n_host, ", ".join(str(sum(h["lens"])) for h in host[::nt]))},
+                    "batches": "%d distinct pinned host batches in rotation (same length profile as the "
+                               "resident batch, T = %d; different ids / features / masks)"
+                               % (n_host, sum(lens0))},
             "step_mode": ("eager (Python enqueues every launch)" if graphed is None else
                           "cuda_graph: fwd+bwd%s replayed per token bucket of %d (%d graphs captured, "
                           "dummy-sequence padding)" % (" + gradient all-reduce" if ar_mode == "in-graph" else

@@ -445,7 +445,9 @@ def test_full_size_c2_forward_vs_oracle_and_batch_invariance():
                                  batch["attn_masks"], batch["gather_index"], output_all_encoded_layers=False)
     v = _valid(batch)
     err = (out - ref)[v].abs()
-    assert err.max().item() <= 2e-2 and err.mean().item() <= 2e-3, (err.max().item(), err.mean().item())
+    # 12 layers in fp16: the reference's own fp16 arithmetic is 2.2e-2 away from fp32 here (measured in
+    # tests/test_c2_parity_gpu.py, which states the bound precisely); this test guards the batch invariance
+    assert err.max().item() <= 2.5e-2 and err.mean().item() <= 2e-3, (err.max().item(), err.mean().item())
     lens = [a + b for a, b in zip(batch["txt_lens"], batch["num_bbs"])]
     for k in (max(range(64), key=lambda i: lens[i]), min(range(64), key=lambda i: lens[i])):
         tl, nb = batch["txt_lens"][k], batch["num_bbs"][k]
