@@ -700,14 +700,13 @@ extern "C" int ub200_attn_fwd(const ub200_attn_args* args, ub200_stream_t stream
       single ? (bf ? attn_fwd_kernel<true, true> : attn_fwd_kernel<false, true>)
              : (bf ? attn_fwd_kernel<true, false> : attn_fwd_kernel<false, false>);
   const int smem_bytes = single ? ATT_FWD_SMEM_SINGLE : ATT_FWD_SMEM;
-  static bool configured[4] = {false, false, false, false};
+  static unsigned long long configured[4] = {0, 0, 0, 0};   // one bit per device
   const int ci = (single ? 2 : 0) + (bf ? 1 : 0);
-  if (!configured[ci]) {
+  if (first_use_on_device(configured[ci])) {
     UB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     if (single)   // 4 CTAs x 49 KB per SM: ask for the full shared-memory carve-out
       UB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared));
-    configured[ci] = true;
   }
   {
     ProfScope ps(stream);
@@ -777,14 +776,13 @@ extern "C" int ub200_attn_bwd(const ub200_attn_args* args, ub200_stream_t stream
       single ? (di ? attn_bwd_kernel<true, true> : attn_bwd_kernel<false, true>)
              : (di ? attn_bwd_kernel<true, false> : attn_bwd_kernel<false, false>);
   const int smem_bytes = single ? ATT_BWD_SMEM_SINGLE : ATT_BWD_SMEM;
-  static bool configured[4] = {false, false, false, false};
+  static unsigned long long configured[4] = {0, 0, 0, 0};   // one bit per device
   const int ci = (single ? 2 : 0) + di;
-  if (!configured[ci]) {
+  if (first_use_on_device(configured[ci])) {
     UB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     if (single)
       UB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared));
-    configured[ci] = true;
   }
   {
     ProfScope ps(stream);

@@ -25,6 +25,17 @@ int set_error(int code, const char* fmt, ...);  // stores message, returns code
 
 int num_sms();  // SM count of the current device (cached)
 
+// cudaFuncSetAttribute is per DEVICE: one bit per device in a per-instantiation mask (a process that
+// drives several GPUs configures each of them once).  Returns true the first time for this device.
+inline bool first_use_on_device(unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 // 2-D row-major tensor [rows, cols] of 16-bit elements with row pitch `ld` (elements);
 // box = box_cols x box_rows, 128-byte swizzle, zero OOB fill.  Returns 0 / negative code.
 int make_tma_2d(CUtensorMap* out, const void* base, int dtype, uint64_t rows, uint64_t cols,

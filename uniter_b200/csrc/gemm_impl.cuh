@@ -770,12 +770,10 @@ static int launch_gemm(const GemmParams& p, const CUtensorMap& tmA, const CUtens
   void (*kern)(const CUtensorMap, const CUtensorMap, const GemmParams);
   if (kCluster == 2) kern = gemm2sm_kernel<BN, A_MN, B_MN, kBF16, EPI>;
   else kern = gemm_kernel<BN, A_MN, B_MN, kBF16, EPI>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static unsigned long long configured = 0;  // per instantiation, one bit per device
+  if (first_use_on_device(configured))
     UB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
-    configured = true;
-  }
   {
     ProfScope ps(stream);
     UB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, kCluster,
@@ -840,12 +838,10 @@ int gemm_group_launch(const TmPack& tm, const GroupedParams& g, int grid, cudaSt
   if (g.epilogue == 0) kern = gemm_group_kernel<BN, kBF16, 0>;
   else if (g.epilogue == UB200_EPI_ACCUM) kern = gemm_group_kernel<BN, kBF16, UB200_EPI_ACCUM>;
   else return set_error(UB200_EUNSUPPORTED, "gemm_grouped: epilogue must be 0 or ACCUM");
-  static bool configured[2] = {false, false};   // per instantiation
+  static unsigned long long configured[2] = {0, 0};   // per instantiation, one bit per device
   const int ci = g.epilogue ? 1 : 0;
-  if (!configured[ci]) {
+  if (first_use_on_device(configured[ci]))
     UB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured[ci] = true;
-  }
   ProfScope ps(stream);
   UB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, 1, tm, g));
   return 0;

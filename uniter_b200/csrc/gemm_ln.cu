@@ -314,15 +314,9 @@ static int launch_gemm_ln_t(const GemmParams& p, const LnEpiParams& q, const CUt
                             const CUtensorMap& tmB, cudaStream_t stream) {
   using Cfg = GemmLnCfg<BN>;
   auto kern = gemm_ln_kernel<BN, kBF16, kDrop>;
-  static bool configured = false;   // per instantiation; the attribute is per device, set again below
-  static int configured_dev = -1;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!configured || configured_dev != dev) {
+  static unsigned long long configured = 0;   // per instantiation, one bit per device
+  if (first_use_on_device(configured))
     UB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-    configured_dev = dev;
-  }
   const int grid = p.tiles_m * LN_CLUSTER;
   ProfScope ps(stream);
   UB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, LN_CLUSTER, tmA,
