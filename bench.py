@@ -33,6 +33,7 @@ C2 = dict(B=64, tl=(12, 28), nbb=(26, 46), seed=1234, mlm_prob=0.15)
 # BASELINE.json configs.  The default (and the driver's) run is C2, the config the
 # metric is quoted on; the others are reachable with --config for the profiles / docs.
 CONFIGS = {
+    "c3": dict(label="C3"),
     "c5": dict(label="C5"),
     "c2": dict(label="C2", arch=BASE, arch_name="UNITER-base", metric=METRIC, tasks=("mlm",),
                B=64, tl=(12, 28), nbb=(26, 46), seed=1234, mlm_prob=0.15, mrm_prob=0.15),
@@ -67,7 +68,8 @@ def parse():
                     help="graph mode: token counts are padded to a multiple of this with a dummy sequence")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS),
                     help="c2 (default, the metric's config): UNITER-base MLM; c4: UNITER-large 24-layer "
-                         "pre-training step, tasks cycled mlm -> mrfr -> mrc-kl -> itm; c5: UNITER-base ITM "
+                         "pre-training step, tasks cycled mlm -> mrfr -> mrc-kl -> itm; c3: UNITER-base VQA fine-tuning, 5 accumulated "
+                         "micro-batches of <= 5120 padded tokens; c5: UNITER-base ITM "
                          "hard-negative iteration (400-pair no-grad scoring + 32-pair train step, both directions)")
     ap.add_argument("--layers", type=int, default=0, help=argparse.SUPPRESS)
     return ap.parse_args()
@@ -224,6 +226,153 @@ def cpu_reference_run(args, steps, warmup, sample_B):
                           "UNMODIFIED reference UniterForPretraining('mlm') from oracle/_ref" if kind == "reference"
                           else "oracle port (reference sources not staged)",
                           best_n, os.cpu_count() or 1, os.cpu_count() or 1))
+
+
+# =============================================================================== C3: VQA fine-tuning
+def bench_c3(args, real_out, rank, world, local_rank):
+    """BASELINE.json configs[2]: UNITER-base VQA fine-tuning with the shapes of
+    config/train-vqa-base-4gpu.json (train_vqa.py:183-229): per GPU a micro-batch of <= 5120 PADDED
+    tokens with a sample count that is a multiple of 8 (TokenBucketSampler, data/sampler.py:31-57),
+    text 5..22 tokens + 10..100 regions, 3129 answers, soft targets; 5 micro-batches are accumulated
+    per optimizer step and the gradients all-reduced once (gradient_accumulation_steps = 5).
+    One STEP here = those 5 micro-batches (fwd + bwd each, accumulated in the gradient arena) + the
+    all-reduce for N > 1.  Each micro-batch is a CUDA-graph replay (first: overwrite, others:
+    accumulate); the VQA classifier (model/vqa.py:23-28) is torch over the library pooler."""
+    import random
+    import torch.distributed as dist
+    from torch.nn import functional as F
+    from uniter_b200 import _lib
+    from uniter_b200 import distributed as ubd
+    from uniter_b200.arena import GradArena
+    from uniter_b200.batching import TokenBucketSampler
+    from uniter_b200.graphed import GraphedStep
+    from uniter_b200.heads import UniterForVisualQuestionAnswering
+    from uniter_b200.model import UniterConfig
+    from uniter_b200.synth import synth_batch
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    _lib.check(lib.ub200_device_check())
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+    NA, ACC, MAXTOK = 3129, 5, 5120
+    torch.manual_seed(0)
+    NLr = args.layers or BASE["NL"]
+    cfg = UniterConfig(BASE["vocab"], hidden_size=BASE["H"], num_hidden_layers=NLr,
+                       num_attention_heads=BASE["heads"], intermediate_size=BASE["I"],
+                       max_position_embeddings=BASE["max_pos"])
+    model = UniterForVisualQuestionAnswering(cfg, BASE["img_dim"], NA).to(dev, dtype).train()
+    if world > 1:
+        ubd.broadcast_parameters(model, root=0)
+    GradArena.attach(model)
+    reducer = ubd.GradientReducer(model, overlap_chunks=1) if world > 1 else None
+
+    # a pool of examples with the config's length ranges, batched by the reference's own sampler logic
+    g = torch.Generator().manual_seed(1000 + rank)
+    n_pool = 2048
+    tls = torch.randint(5, 23, (n_pool,), generator=g).tolist()
+    nbs = torch.randint(10, 101, (n_pool,), generator=g).tolist()
+    lens_pool = [a + b for a, b in zip(tls, nbs)]
+    batches = list(iter(TokenBucketSampler(lens_pool, bucket_size=8192, batch_size=MAXTOK, droplast=True,
+                                           rng=random.Random(7 + rank))))
+    host = []
+    for ids in batches[:ACC]:
+        b = synth_batch(len(ids), 0, 0, 0, 0, seed=300 + len(host), txt_lens=[tls[i] for i in ids],
+                        num_bbs=[nbs[i] for i in ids])
+        b["targets"] = torch.rand(len(ids), NA, generator=g)
+        hb = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()}
+        hb["lens"] = [tls[i] + nbs[i] for i in ids]
+        host.append(hb)
+    samples_per_step = sum(len(h["lens"]) for h in host)
+    h2d_bytes = sum(v.numel() * v.element_size() for hb in host for v in hb.values() if torch.is_tensor(v))
+
+    def loss_fn(batch):
+        # train_vqa.py:186-188: loss.mean() * num_answers, divided over the accumulation window by the
+        # optimizer step (delay_unscale) — here folded into the loss
+        l = model(batch, compute_loss=True)
+        return l.float().mean() * NA / ACC
+
+    step = GraphedStep(model, loss_fn)
+    dev_batches = [{k: v.to(dev, non_blocking=True) for k, v in hb.items() if torch.is_tensor(v)} for hb in host]
+    torch.cuda.synchronize()
+
+    def one_step(i, from_host=False):
+        for j, hb in enumerate(host):
+            src = {k: v for k, v in hb.items() if torch.is_tensor(v)} if from_host else dev_batches[j]
+            loss = step(src, hb["lens"], accumulate=j > 0)
+        if reducer is not None:
+            reducer.reduce()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for i in range(max(3, args.warmup)):
+        one_step(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_res = timed(one_step, args.steps) / args.steps
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def e2e(i):
+        l = one_step(i, from_host=True)          # H2D of every micro-batch from pinned memory, in stream
+        loss_host.copy_(l.float().reshape(1), non_blocking=True)
+
+    for i in range(2):
+        e2e(i)
+    ms_e2e = timed(e2e, args.steps) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        flops = sum(algorithmic_flops(h["lens"], NLr, BASE["H"]) for h in host)
+        pk = peaks()
+        launches = sum(b.launches for b in step.buckets.values()) // 2
+        line = {
+            "metric": "uniter_base_vqa_finetune_samples_per_sec",
+            "value": round(samples_per_step * world / (ms_res * 1e-3), 1), "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms_res, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic",
+            "config": {"workload": "C3: UNITER-base VQA fine-tuning (train-vqa-base-4gpu.json shapes): %d "
+                                   "micro-batches of <= 5120 padded tokens (%s samples, text 5..22 + 10..100 "
+                                   "regions, %d valid tokens) accumulated per step, 3129 answers, dropout 0.1"
+                                   % (ACC, "+".join(str(len(h["lens"])) for h in host),
+                                      sum(sum(h["lens"]) for h in host)),
+                       "global_batch": samples_per_step * world, "parallelism": "dp%d" % world},
+            "e2e": {"value": round(samples_per_step * world / (ms_e2e * 1e-3), 1), "unit": "samples/s",
+                    "ms_per_step": round(ms_e2e, 4), "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "step_mode": "cuda_graph per micro-batch (%d graphs), all-reduce after the window" % step.captures,
+            "gpu_launches": int(launches),
+            "algorithmic_tflops_per_step": round(flops / 1e12, 4),
+            "achieved_tflops": round(flops / (ms_res * 1e-3) / 1e12, 1),
+            "roofline": {"bound": "tensor", "kernel": "whole step (encoder GEMMs dominate)",
+                         "achieved": round(flops / (ms_res * 1e-3) / 1e12, 1), "peak": pk["tflops"],
+                         "unit": "TFLOP/s", "frac": round(flops / (ms_res * 1e-3) / 1e12 / pk["tflops"], 4),
+                         "peak_source": pk["source"], "traffic": None},
+            "clocks": clocks,
+        }
+        print(json.dumps(line), file=real_out, flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # =============================================================================== C5: ITM hard negatives
@@ -451,6 +600,8 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     if args.config == "c5":
         return bench_c5(args, real_out, rank, world, local_rank)
+    if args.config == "c3":
+        return bench_c3(args, real_out, rank, world, local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist

@@ -353,10 +353,14 @@ class UniterForVisualQuestionAnswering(UniterPreTrainedModel):
 
     def forward(self, batch, compute_loss=True):
         batch = defaultdict(lambda: None, batch)
-        sequence_output = self.uniter(batch["input_ids"], batch["position_ids"], batch["img_feat"],
-                                      batch["img_pos_feat"], batch["attn_masks"], batch["gather_index"],
-                                      output_all_encoded_layers=False)
-        pooled_output = self.uniter.pooler(sequence_output)
+        # pooler(sequence_output) (model/vqa.py:36-43) from the packed encoder output: only the [CLS]
+        # rows are gathered, the padded [B, L, H] tensor is never materialised
+        packed, meta = self.uniter.encode_packed(
+            batch["input_ids"], batch["position_ids"], batch["img_feat"], batch["img_pos_feat"],
+            batch["attn_masks"], batch["gather_index"], output_all_encoded_layers=False)
+        B, L = meta["n_batch"], meta["L"]
+        cls_rows = meta["unpack_ext"][::L][:B].contiguous()
+        pooled_output = self.uniter.pooler(gather_packed_rows(packed, cls_rows))
         answer_scores = self.vqa_output(pooled_output)
         if compute_loss:
             return F.binary_cross_entropy_with_logits(answer_scores, batch["targets"], reduction="none")
