@@ -171,6 +171,8 @@ class GradArena(object):
         the word embeddings)."""
         self.step_mode = True
         all_ids = list(self._views.keys())
+        if accumulate:
+            self._fresh = set()          # after the window's first step every view is live (or zero)
         if not accumulate:
             if zero_all:
                 self.flat.zero_()
@@ -182,6 +184,18 @@ class GradArena(object):
             v = self._views[id(p)]
             if p.requires_grad and (p.grad is None or p.grad.data_ptr() != v.data_ptr()):
                 p.grad = v
+
+    def finish_step(self):
+        """Explicit protocol, after the backward: library-managed parameters that no writer claimed in
+        this step (a head the step's task does not use, the mask embedding without img_masks, ...)
+        still hold whatever an earlier step left in their views — zero them, so that every .grad is
+        either this step's gradient or exactly zero (their .grad cannot be None: fixed addresses)."""
+        if not self.step_mode:
+            return
+        for p in self._params():
+            if id(p) in self._fresh:
+                self._views[id(p)].zero_()
+        self._fresh = set()
 
     def end_step_mode(self):
         self.step_mode = False

@@ -101,6 +101,7 @@ class GraphedStep(object):
                 self.reducer.backward_and_reduce(loss)
             else:
                 loss.backward()
+            self.arena.finish_step()          # parameters this step never touched: exactly zero
             if self.optimizer is not None:
                 self.optimizer.step(**self.optimizer_kwargs)
         finally:

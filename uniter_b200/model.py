@@ -965,7 +965,8 @@ class UniterModel(UniterPreTrainedModel):
         attached with GradArena.attach(root) (bench / GraphedStep / GradientReducer do that so that
         the task head's gradients live in the same flat buffer)."""
         from .arena import GradArena
-        self._weight_table()
+        if self.encoder.layer[0].attention.self.query.weight.is_cuda:
+            self._weight_table()           # (CPU: host-side bookkeeping only, e.g. the gloo / arena tests)
         if self._arena is None or not self._arena[0]._still_valid():
             self._arena = None
             GradArena(self)                      # binds itself through _bind_arena
