@@ -62,8 +62,11 @@ def parse():
                     help="N>1: SMs left to the overlapped all-reduce (and its CTA cap)")
     ap.add_argument("--no-graph", action="store_true",
                     help="enqueue every step from Python (eager) instead of replaying CUDA graphs")
-    ap.add_argument("--allreduce", default="auto", choices=["auto", "in-graph", "after"],
-                    help="N>1 graph mode: capture the NCCL all-reduces inside the graph (auto: try, else after)")
+    ap.add_argument("--allreduce", default="after", choices=["after", "split", "in-graph"],
+                    help="N>1 graph mode: 'after' = all-reduce the arena after each replay; 'split' = the step is "
+                         "captured as one graph per layer group and each group's slice is all-reduced (eagerly, on a "
+                         "side stream) while the next group's graph runs; 'in-graph' = NCCL captured inside the graph "
+                         "(hangs with this torch / NCCL build: measured, kept for experiments only)")
     ap.add_argument("--token-bucket", type=int, default=128,
                     help="graph mode: token counts are padded to a multiple of this with a dummy sequence")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS),
@@ -699,22 +702,11 @@ def main():
     graphed = None
     if not args.no_graph:
         graphed = GraphedStep(model, loss_fn, token_bucket=args.token_bucket,
-                              reducer=reducer if ar_mode in ("in-graph", "auto") else None)
-        if ar_mode == "auto":
-            ar_mode = "in-graph"
-            try:       # probe: capture + one replay of the first batch's bucket with NCCL inside
-                pb = {k: v for k, v in host[0].items() if torch.is_tensor(v)}
-                bk = graphed.stage(pb, host[0]["lens"], tag=host[0]["task"])
-                bk.graph.replay()
-                torch.cuda.synchronize()
-            except Exception as e:      # noqa: BLE001  (symmetric across ranks: same code, same NCCL)
-                sys.stderr.write("in-graph all-reduce unavailable (%s: %s); reducing after each replay\n"
-                                 % (type(e).__name__, e))
-                ar_mode = "after"
-                graphed = GraphedStep(model, loss_fn, token_bucket=args.token_bucket, reducer=None)
+                              reducer=reducer if ar_mode in ("in-graph", "split") else None,
+                              reducer_mode="split" if ar_mode == "split" else "in-graph")
 
     def replay(bk):
-        bk.graph.replay()
+        graphed.replay(bk)
         if ar_mode == "after":
             reducer.reduce()
 
@@ -955,7 +947,9 @@ def main():
             "step_mode": ("eager (Python enqueues every launch)" if graphed is None else
                           "cuda_graph: fwd+bwd%s replayed per token bucket of %d (%d graphs captured, "
                           "dummy-sequence padding)" % (" + gradient all-reduce" if ar_mode == "in-graph" else
-                                                       (", all-reduce after each replay" if ar_mode == "after" else ""),
+                                                       (", all-reduce after each replay" if ar_mode == "after" else
+                                                        (", one graph per layer group with the previous group's "
+                                                         "all-reduce overlapped" if ar_mode == "split" else "")),
                                                        args.token_bucket, graphed.captures)),
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(cpu_enqueue_ms, 3),
             "algorithmic_tflops_per_step": round(flops_step / 1e12, 4),

@@ -82,6 +82,24 @@ class GradientReducer:
         self._comm_stream = torch.cuda.Stream() if self.arena.flat.is_cuda else None
         self._reserved = False
         self._bwd_seen = {}
+        # GraphedStep (split mode) sets this while it CAPTURES a step: instead of issuing NCCL, the
+        # reducer reports which arena ranges become final at this point of the backward
+        self._split_cb = None
+
+    def _emit(self, ranges, final=False):
+        ranges = [(lo, hi) for lo, hi in ranges if hi > lo]
+        if self._split_cb is not None:
+            self._split_cb(ranges, final)
+            self._done += ranges
+        else:
+            for lo, hi in ranges:
+                self._ship(lo, hi)
+
+    def ship(self, ranges):
+        """Issue the all-reduces of these arena ranges now (side stream, after everything enqueued on the
+        current stream so far): the replay side of a step captured in split mode."""
+        for lo, hi in ranges:
+            self._ship(lo, hi)
 
     # ---- overlap: called by _EncoderStack.backward after the kernels of layers [lo, hi) are enqueued
     def _ship(self, lo, hi):
@@ -111,14 +129,16 @@ class GradientReducer:
             return
         ei = self.encoders.index(enc)
         _, ep = enc._ensure_arena()
+        ranges = []
         if hi == NL:
             # everything downstream of the encoder output (task head, pooler) has finished its backward
             h_lo, h_hi = self.arena.segments["head"]
             p_lo, p_hi = self.arena.segments["enc%d.pooler" % ei]
             if ei == 0 and len(self.encoders) == 1 and h_hi == p_lo:
                 self.arena.fold_foreign_range(h_lo, p_hi)
-                self._ship(h_lo, p_hi)
-        self._ship(ep["layer0"] + lo * ep["per_layer"], ep["layer0"] + hi * ep["per_layer"])
+                ranges.append((h_lo, p_hi))
+        ranges.append((ep["layer0"] + lo * ep["per_layer"], ep["layer0"] + hi * ep["per_layer"]))
+        self._emit(ranges)
 
     def reduce(self):
         """Ship whatever part of the arena has not been shipped yet, then wait for everything."""
@@ -130,6 +150,13 @@ class GradientReducer:
             pos = max(pos, hi)
         if pos < self.arena.numel:
             rest.append((pos, self.arena.numel))
+        if self._split_cb is not None:          # capturing in split mode: report, issue nothing
+            self._emit(rest, final=True)
+            self._done = []
+            self._bwd_seen = {}
+            for enc in self.encoders:
+                enc._fwd_since_reduce = 0
+            return
         works = self._pending
         self._pending = []
         cuda = self.arena.flat.is_cuda

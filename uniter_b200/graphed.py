@@ -37,22 +37,30 @@ def _round_up(v, m):
 
 
 class _Bucket(object):
-    __slots__ = ("graph", "inputs", "meta_dev", "meta_offs", "loss", "T_pad", "maxseq", "n_replays",
-                 "launches")
+    __slots__ = ("graph", "graphs", "ship_after", "inputs", "meta_dev", "meta_offs", "loss", "T_pad", "maxseq",
+                 "n_replays", "launches")
 
 
 class GraphedStep(object):
     def __init__(self, module, loss_fn, token_bucket=128, reducer=None, optimizer=None,
-                 optimizer_kwargs=None, zero_all_grads=False, mask_key="attn_masks", warmup=2):
+                 optimizer_kwargs=None, zero_all_grads=False, mask_key="attn_masks", warmup=2,
+                 reducer_mode="split"):
         """module: the root nn.Module (its parameters' gradients go to one arena);
         loss_fn(batch_on_device) -> scalar loss (runs the forward);
-        reducer: optional GradientReducer — its all-reduces are captured inside the graph, overlapped
-        with the backward exactly as in eager mode; optimizer: optional FusedAdamW stepped inside the
-        graph; zero_all_grads: see GradArena.begin_step(zero_all=...)."""
+        reducer: optional GradientReducer.  reducer_mode "split" (default): the step is captured as a
+        CHAIN of graphs cut where a slice of the gradient arena becomes final (after the task head +
+        top layer group, after every further layer group, after the embedding backward); on replay each
+        slice's NCCL all-reduce is issued eagerly on the reducer's side stream right after its graph and
+        overlaps the next graph; the tail graph (never-touched gradients zeroed, optimizer) runs after
+        the last all-reduce.  "in-graph": NCCL captured inside one graph (hangs with torch 2.11 /
+        NCCL 2.28 in this environment — kept for experiments).
+        optimizer: optional FusedAdamW stepped inside the (tail) graph; zero_all_grads: see
+        GradArena.begin_step(zero_all=...)."""
         self.module = module
         self.loss_fn = loss_fn
         self.token_bucket = int(token_bucket)
         self.reducer = reducer
+        self.reducer_mode = reducer_mode if reducer is not None else "none"
         self.optimizer = optimizer
         self.optimizer_kwargs = optimizer_kwargs or {}
         self.zero_all = bool(zero_all_grads)
@@ -142,20 +150,80 @@ class GraphedStep(object):
         self.optimizer = opt
         if opt is not None:
             opt.prepare()
-        g = torch.cuda.CUDAGraph()
         if self.pool is None:
             self.pool = torch.cuda.graph_pool_handle()
         from . import _lib
         lib = _lib.load()
         lib.ub200_launch_count.restype = __import__("ctypes").c_ulonglong
         n0 = lib.ub200_launch_count()
-        with torch.cuda.graph(g, pool=self.pool):
-            bk.loss = self._run(bk, accumulate, tag)
+        if self.reducer_mode == "split":
+            self._capture_split(bk, accumulate, tag)
+        else:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.pool):
+                bk.loss = self._run(bk, accumulate, tag)
+            bk.graphs, bk.ship_after = [g], [[]]
         bk.launches = int(lib.ub200_launch_count() - n0)     # libub200 kernels inside one replay
-        bk.graph = g
+        bk.graph = bk.graphs[0]
         self.buckets[key] = bk
         self.captures += 1
         return bk
+
+    def _capture_split(self, bk, accumulate, tag):
+        """Capture the step as a chain of graphs, cut wherever the reducer reports that ranges of the
+        arena are final (reducer._split_cb).  No NCCL call happens during the capture; on replay the
+        ranges recorded for a cut are all-reduced right after the graph that ends there."""
+        import gc
+        graphs, ship = [], []
+        state = {"g": None}
+
+        def begin():
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin(pool=self.pool)
+            state["g"] = g
+
+        def cut(ranges, final=False):
+            state["g"].capture_end()
+            graphs.append(state["g"])
+            ship.append(list(ranges))
+            begin()                       # (after the final cut: the tail — zeroing, optimizer)
+
+        torch.cuda.synchronize()
+        gc.collect()
+        cap = torch.cuda.Stream()
+        cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cap):
+            begin()
+            self.reducer._split_cb = cut
+            try:
+                # the cuts end / begin captures from inside autograd's backward: keep it on this thread
+                with torch.autograd.set_multithreading_enabled(False):
+                    bk.loss = self._run(bk, accumulate, tag)
+            finally:
+                self.reducer._split_cb = None
+                state["g"].capture_end()
+                graphs.append(state["g"])
+                ship.append([])
+        torch.cuda.current_stream().wait_stream(cap)
+        bk.graphs, bk.ship_after = graphs, ship
+
+    def replay(self, bk):
+        """Enqueue one step of a staged bucket (see stage())."""
+        if self.optimizer is not None:
+            self.optimizer.sync_lr()          # the captured step reads the learning rates from the device
+        if len(bk.graphs) == 1:
+            bk.graphs[0].replay()
+        else:
+            red = self.reducer
+            last = len(bk.graphs) - 1
+            for k, g in enumerate(bk.graphs):
+                if k == last:
+                    red.reduce()              # nothing left to ship: waits for the slices in flight
+                g.replay()
+                if bk.ship_after[k]:
+                    red.ship(bk.ship_after[k])
+        bk.n_replays += 1
+        return bk.loss
 
     # ------------------------------------------------------------------ public
     def stage(self, host_batch, lens, accumulate=False, tag=None):
@@ -175,9 +243,4 @@ class GraphedStep(object):
         return bk
 
     def __call__(self, batch, lens, accumulate=False, tag=None):
-        bk = self.stage(batch, lens, accumulate, tag)
-        if self.optimizer is not None:
-            self.optimizer.sync_lr()          # the captured step reads the learning rates from the device
-        bk.graph.replay()
-        bk.n_replays += 1
-        return bk.loss
+        return self.replay(self.stage(batch, lens, accumulate, tag))
