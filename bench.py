@@ -62,11 +62,18 @@ def parse():
                     help="N>1: SMs left to the overlapped all-reduce (and its CTA cap)")
     ap.add_argument("--no-graph", action="store_true",
                     help="enqueue every step from Python (eager) instead of replaying CUDA graphs")
-    ap.add_argument("--allreduce", default="after", choices=["after", "split", "in-graph"],
-                    help="N>1 graph mode: 'after' = all-reduce the arena after each replay; 'split' = the step is "
+    ap.add_argument("--allreduce", default="after", choices=["after", "split", "in-graph", "peer"],
+                    help="N>1 graph mode: 'peer' = the gradient slices are exchanged by the library's own NVLink "
+                         "peer-memory kernel (csrc/peer.cu) as nodes of the step's ONE graph, overlapped with the "
+                         "backward (falls back to 'after' if the start-up self-test of the exchange fails); "
+                         "'after' = NCCL all-reduce of the arena after each replay; 'split' = the step is "
                          "captured as one graph per layer group and each group's slice is all-reduced (eagerly, on a "
                          "side stream) while the next group's graph runs; 'in-graph' = NCCL captured inside the graph "
                          "(hangs with this torch / NCCL build: measured, kept for experiments only)")
+    ap.add_argument("--peer-ctas", type=int, default=32,
+                    help="--allreduce peer: CTAs (256 threads) of an exchange kernel that overlaps the backward")
+    ap.add_argument("--peer-tail-ctas", type=int, default=64,
+                    help="--allreduce peer: CTAs of the exchange kernels issued after the backward")
     ap.add_argument("--token-bucket", type=int, default=128,
                     help="graph mode: token counts are padded to a multiple of this with a dummy sequence")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS),
@@ -161,6 +168,41 @@ def _probe_threads(one_step):
             break
     torch.set_num_threads(best_n)
     return best_n
+
+
+def peer_selftest(dev):
+    """Start-up check of the NVLink peer-memory exchange (collective): cudaIpc mapping works on this
+    box and three all-reduces of a small buffer give the NCCL result.  (ok, reason) — identical on
+    every rank, so that all ranks take the same path."""
+    import torch.distributed as dist
+    from uniter_b200 import distributed as ubd
+    ok, why = 1.0, ""
+    try:
+        n = 8 << 20                     # 16 MB: its own cudaMalloc segment of the caching allocator
+        flat = torch.zeros(n, device=dev, dtype=torch.bfloat16)
+        px = ubd.PeerExchange(flat, timeout_ms=3000)
+        g = torch.Generator(device=dev).manual_seed(7 + dist.get_rank())
+        for rep in range(3):
+            flat.copy_(torch.randn(n, device=dev, generator=g).to(torch.bfloat16))
+            want = flat.float()
+            dist.all_reduce(want, op=dist.ReduceOp.SUM)
+            want = (want / dist.get_world_size()).to(torch.bfloat16)
+            px.all_reduce(0, n)
+            torch.cuda.synchronize()
+            if px.error_word() != 0:
+                ok, why = 0.0, "flag wait expired"
+                break
+            if not torch.allclose(flat.float(), want.float(), rtol=8e-3, atol=1e-6):
+                ok, why = 0.0, "wrong result"
+                break
+        px.close()
+    except Exception as e:            # mapping refused (no peer access / ipc disabled in this container)
+        ok, why = 0.0, "%s: %s" % (type(e).__name__, str(e)[:120])
+    t = torch.tensor([ok], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if t.item() != 1.0 and not why:
+        why = "failed on another rank"
+    return t.item() == 1.0, why
 
 
 def cpu_reference_run(args, steps, warmup, sample_B):
@@ -640,7 +682,17 @@ def main():
     if world > 1:
         ubd.broadcast_parameters(model, root=0)
     GradArena.attach(model)          # one flat gradient buffer: head | pooler | layers | front-end
-    reducer = (ubd.GradientReducer(model, overlap_chunks=args.overlap_chunks, sm_reserve=args.sm_reserve)
+    peer_note = None
+    if world > 1 and args.allreduce == "peer":
+        ok, why = peer_selftest(dev)
+        if not ok:
+            peer_note = "peer exchange self-test failed (%s): NCCL all-reduce after each replay instead" % why
+            args.allreduce = "after"
+            if rank == 0:
+                print("bench: " + peer_note, file=sys.stderr)
+    reducer = (ubd.GradientReducer(model, overlap_chunks=args.overlap_chunks, sm_reserve=args.sm_reserve,
+                                   transport="peer" if args.allreduce == "peer" else "nccl",
+                                   peer_ctas=args.peer_ctas, peer_tail_ctas=args.peer_tail_ctas)
                if world > 1 else None)
 
     # ---- synthetic batches (per-rank seed), host side pinned; masked-token / masked-region lists are
@@ -702,7 +754,7 @@ def main():
     graphed = None
     if not args.no_graph:
         graphed = GraphedStep(model, loss_fn, token_bucket=args.token_bucket,
-                              reducer=reducer if ar_mode in ("in-graph", "split") else None,
+                              reducer=reducer if ar_mode in ("in-graph", "split", "peer") else None,
                               reducer_mode="split" if ar_mode == "split" else "in-graph")
 
     def replay(bk):
@@ -837,6 +889,11 @@ def main():
     clocks = sampler.stop() if rank == 0 else None     # sampled across both timed regions (under load)
     assert all(l == l for l in losses), "NaN loss in the e2e leg"
     e2e_value = CF["B"] * world / (ms_e2e * 1e-3)
+    peer_err = 0
+    if reducer is not None and reducer.peer is not None:
+        t = torch.tensor([float(reducer.peer.error_word() != 0)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        peer_err = int(t.item())
 
     def step(i):                                       # eager step for the per-launch event pass
         return eager_step(resident[i % nt], host[i % nt]["lens"], tasks[i % nt])
@@ -947,9 +1004,11 @@ def main():
             "step_mode": ("eager (Python enqueues every launch)" if graphed is None else
                           "cuda_graph: fwd+bwd%s replayed per token bucket of %d (%d graphs captured, "
                           "dummy-sequence padding)" % (" + gradient all-reduce" if ar_mode == "in-graph" else
+                                                       (" + gradient exchange (NVLink peer-memory kernels "
+                                                        "overlapping the backward, no NCCL)" if ar_mode == "peer" else
                                                        (", all-reduce after each replay" if ar_mode == "after" else
                                                         (", one graph per layer group with the previous group's "
-                                                         "all-reduce overlapped" if ar_mode == "split" else "")),
+                                                         "all-reduce overlapped" if ar_mode == "split" else ""))),
                                                        args.token_bucket, graphed.captures)),
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(cpu_enqueue_ms, 3),
             "algorithmic_tflops_per_step": round(flops_step / 1e12, 4),
@@ -957,6 +1016,15 @@ def main():
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "train_step": train_step,
             "breakdown": breakdown,
         }
+        if world > 1:
+            line["gradient_exchange"] = {
+                "mode": ar_mode,
+                "transport": "ub::peer_allreduce_kernel over cudaIpc-mapped NVLink peer memory" if ar_mode == "peer"
+                             else "ncclAllReduce(AVG) on slices of the gradient arena",
+                "bytes_per_rank_per_step": int(GradArena.attach(model).numel) * 2,
+                "note": peer_note}
+            if peer_err:
+                line["invalid"] = "a flag wait of the peer exchange expired: the gradients of this run are not reduced"
         print(json.dumps(line), file=real_out, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -445,6 +445,47 @@ int ub200_adamw_step(const ub200_adam_segment* segs_dev, const int32_t* blk_star
                      float max_norm, const float* sumsq, const ub200_adam_state* state_dev,
                      const float* lr_dev, ub200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Gradient exchange over NVLink peer memory — replaces utils/distributed.py:16-43
+ * (all_reduce_and_rescale_tensors: flatten -> hvd.allreduce_ = mean over ranks -> unflatten; call
+ * sites train_vqa.py:193-199, pretrain.py:302-308) with ONE kernel per slice of the flat gradient
+ * arena: push my copy of sub-slice q to rank q's staging buffer, flag barrier, reduce sub-slice
+ * `rank` in fp32 (rank order 0..world-1, so every rank ends up with bit-identical values), write
+ * it into every rank's arena, flag barrier.  Only posted stores cross NVLink; the kernel is an
+ * ordinary node of the step's CUDA graph (no host, no NCCL) and small enough (256 threads x <= 64
+ * registers, no shared memory) to share SMs with the persistent GEMM CTAs of the backward pass it overlaps.
+ *
+ * Memory (caller-owned, one set per rank, mapped into every process with the ipc calls below):
+ *   buf[q]   rank q's arena base (16-bit elements); the slice is [offset, offset + count)
+ *   stage[q] rank q's staging buffer, >= ub200_peer_stage_bytes(count, world) bytes
+ *   flags[q] rank q's signal block, ub200_peer_flags_bytes() bytes, zero-initialised ONCE (epochs
+ *            are monotonic); word 19 is a sticky error word: non-zero after a wait expired
+ *            (value = (call number << 4) | phase) — the data of that and later calls is invalid.
+ * Every rank must issue the same sequence of calls (same offset / count), one at a time per rank. */
+#define UB200_MAX_PEERS 8
+typedef struct {
+  void* buf[UB200_MAX_PEERS];
+  void* stage[UB200_MAX_PEERS];
+  uint32_t* flags[UB200_MAX_PEERS];
+  int32_t rank, world;
+  int64_t offset, count;     /* elements; both multiples of 8 (16 bytes) */
+  int64_t stage_bytes;       /* size of each staging buffer */
+  int32_t dtype;             /* UB200_F16 / UB200_BF16 */
+  int32_t max_ctas;          /* CTAs (256 threads each) the exchange may use (0: 32) */
+  float scale;               /* result = scale * sum over ranks; 1/world = Horovod's average */
+  int32_t timeout_ms;        /* bound of every flag wait (0: 20 s) */
+} ub200_peer_allreduce_args;
+int64_t ub200_peer_flags_bytes(void);
+int64_t ub200_peer_stage_bytes(int64_t count, int32_t world);
+int ub200_peer_allreduce(const ub200_peer_allreduce_args* args, ub200_stream_t stream);
+/* cudaIpc plumbing for device memory owned by the caller (e.g. a torch caching-allocator block):
+ * export gives the 64-byte handle of the ALLOCATION containing dev_ptr and dev_ptr's byte offset in
+ * it; open maps that allocation into this process (peer access is enabled lazily) and returns its
+ * base; an allocation may be opened once per process. */
+int ub200_peer_ipc_export(const void* dev_ptr, void* handle64, int64_t* offset_bytes);
+int ub200_peer_ipc_open(const void* handle64, void** mapped_base);
+int ub200_peer_ipc_close(void* mapped_base);
+
 #ifdef __cplusplus
 }
 #endif

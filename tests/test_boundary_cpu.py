@@ -72,11 +72,12 @@ def test_ctypes_mirrors_match_the_header_layout():
     #include <stddef.h>
     #include "ub200.h"
     int main(void) {
-      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ub200_gemm_args), sizeof(ub200_attn_args),
+      printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ub200_gemm_args), sizeof(ub200_attn_args),
              sizeof(ub200_ln_bwd_args), sizeof(ub200_layer_weights), sizeof(ub200_layer_grads),
              sizeof(ub200_encoder_desc), sizeof(ub200_adam_segment), sizeof(ub200_embed_colsum_args),
              offsetof(ub200_gemm_args, k_splits), offsetof(ub200_gemm_args, n_valid),
-             offsetof(ub200_adam_segment, step_size), offsetof(ub200_embed_colsum_args, T));
+             offsetof(ub200_adam_segment, step_size), offsetof(ub200_embed_colsum_args, T),
+             sizeof(ub200_peer_allreduce_args), offsetof(ub200_peer_allreduce_args, stage_bytes));
       return 0;
     }'''
     with tempfile.TemporaryDirectory() as d:
@@ -89,7 +90,8 @@ def test_ctypes_mirrors_match_the_header_layout():
             C.sizeof(_LayerWeights), C.sizeof(_LayerGrads), C.sizeof(_EncoderDesc),
             C.sizeof(_lib.AdamSegment), C.sizeof(_lib.EmbedColsumArgs),
             _lib.GemmArgs.k_splits.offset, _lib.GemmArgs.n_valid.offset,
-            _lib.AdamSegment.step_size.offset, _lib.EmbedColsumArgs.T.offset]
+            _lib.AdamSegment.step_size.offset, _lib.EmbedColsumArgs.T.offset,
+            C.sizeof(_lib.PeerAllreduceArgs), _lib.PeerAllreduceArgs.stage_bytes.offset]
     assert sizes == mine, (sizes, mine)
 
 

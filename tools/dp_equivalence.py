@@ -2,7 +2,10 @@
 (the reference's own "gradient accumulation emulates multi-gpu" equivalence, README.md:115).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29533 tools/dp_equivalence.py [--graph]
+        --master-port 29533 tools/dp_equivalence.py [--graph] [--peer]
+
+--peer: the slices travel through the library's own NVLink peer-memory kernel (PeerExchange,
+csrc/peer.cu) instead of NCCL; with --graph the exchange kernels are nodes of the step's one graph.
 
 Every rank r computes the gradients of shard r (dropout off) and the GradientReducer averages them
 over NCCL (overlapped chunked all-reduce of arena slices, exactly the bench path; with --graph the
@@ -27,6 +30,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     use_graph = "--graph" in sys.argv
+    use_peer = "--peer" in sys.argv
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
@@ -52,10 +56,13 @@ def main():
     def loss_fn(b):
         return (model(b).sum() * b["mlm_inv_n"]).squeeze()
 
-    reducer = ubd.GradientReducer(model, overlap_chunks=2)
+    reducer = ubd.GradientReducer(model, overlap_chunks=2, transport="peer" if use_peer else "nccl")
+    if use_peer:
+        reducer.peer.timeout_ms = 5000
     hb, lens = shard(rank)
     if use_graph:
-        step = GraphedStep(model, loss_fn, token_bucket=64, reducer=reducer)
+        step = GraphedStep(model, loss_fn, token_bucket=64, reducer=reducer,
+                           reducer_mode="in-graph" if use_peer else "split")
         step(hb, lens)
         step(hb, lens)                                # a second replay: same result, nothing accumulates
     else:
@@ -64,6 +71,7 @@ def main():
         model.zero_grad(set_to_none=True)
         reducer.backward_and_reduce(loss_fn(b))
     torch.cuda.synchronize()
+    peer_err = reducer.peer.error_word() if use_peer else 0
     got = arena.flat.float().clone()
     # every rank must hold the same reduced gradients
     ref0 = got.clone()
@@ -89,8 +97,9 @@ def main():
         den = want.norm().item()
         rec = {"world": world, "graph": use_graph, "rel_err": num / den, "grad_norm": den,
                "max_abs": (got - want).abs().max().item(), "ranks_identical": bool(flags.item() == 1.0),
-               "arena_elements": int(arena.numel)}
-        ok = rec["rel_err"] < 5e-3 and rec["ranks_identical"]
+               "arena_elements": int(arena.numel), "transport": "peer" if use_peer else "nccl",
+               "peer_error_word": peer_err}
+        ok = rec["rel_err"] < 5e-3 and rec["ranks_identical"] and peer_err == 0
         print(json.dumps(rec), flush=True)
     dist.barrier()
     dist.destroy_process_group()

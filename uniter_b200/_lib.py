@@ -96,6 +96,18 @@ class AdamSegment(C.Structure):
                 ("flags", C.c_int32)]
 
 
+MAX_PEERS = 8
+
+
+class PeerAllreduceArgs(C.Structure):
+    _fields_ = [("buf", C.c_void_p * MAX_PEERS), ("stage", C.c_void_p * MAX_PEERS),
+                ("flags", C.POINTER(C.c_uint32) * MAX_PEERS),
+                ("rank", C.c_int32), ("world", C.c_int32),
+                ("offset", C.c_int64), ("count", C.c_int64), ("stage_bytes", C.c_int64),
+                ("dtype", C.c_int32), ("max_ctas", C.c_int32), ("scale", C.c_float),
+                ("timeout_ms", C.c_int32)]
+
+
 F32 = 2
 _lib = None
 
@@ -170,6 +182,17 @@ def load():
     lib.ub200_adam_prep.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ub200_gather_rows.restype = C.c_int
     lib.ub200_gather_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    lib.ub200_peer_flags_bytes.restype = C.c_int64
+    lib.ub200_peer_stage_bytes.restype = C.c_int64
+    lib.ub200_peer_stage_bytes.argtypes = [C.c_int64, C.c_int32]
+    lib.ub200_peer_allreduce.restype = C.c_int
+    lib.ub200_peer_allreduce.argtypes = [C.POINTER(PeerAllreduceArgs), C.c_void_p]
+    lib.ub200_peer_ipc_export.restype = C.c_int
+    lib.ub200_peer_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+    lib.ub200_peer_ipc_open.restype = C.c_int
+    lib.ub200_peer_ipc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.ub200_peer_ipc_close.restype = C.c_int
+    lib.ub200_peer_ipc_close.argtypes = [C.c_void_p]
     _lib = lib
     return lib
 

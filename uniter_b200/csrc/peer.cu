@@ -1,0 +1,308 @@
+// Gradient all-reduce over NVLink peer memory: ONE kernel per arena slice, no NCCL, no host.
+//
+// Replaces the Horovod call of the reference's data-parallel path
+// (utils/distributed.py:16-43: flatten -> hvd.allreduce_ (mean) -> unflatten; call sites
+// train_vqa.py:193-199, pretrain.py:302-308).  Every rank holds the same flat gradient arena
+// (uniter_b200/arena.py); the arenas, one staging buffer and one 256-byte signal block per rank
+// are mapped into every process with cudaIpc (NVSwitch: every peer at full bandwidth).
+//
+// Why not NCCL here.  The exchange has to overlap the backward pass, whose persistent tcgen05 GEMM
+// CTAs own one SM each.  NCCL's kernels (640 threads x ~96 registers) cannot share an SM with a GEMM
+// CTA, so they displace CTAs of the next persistent launch by a whole round; their launch also
+// needs the host (the capture of NCCL inside the step's CUDA graph hangs with this torch / NCCL
+// build).  This kernel is 256 threads x <= 64 registers and no shared memory — 16 K registers, so it
+// co-resides with a GEMM CTA (512 x 80) — and it is an ordinary kernel node of the step's graph.
+//
+// Algorithm (two-shot, push based: only posted stores cross NVLink, so a few CTAs fill the links):
+//   the slice [offset, offset+count) is cut into `world` sub-slices of `per` 16-byte vectors;
+//   A  push   : rank r copies its sub-slice q (q != r) into stage_q[r]              (remote stores)
+//      barrier 1: signal PUSH[r] = epoch on every peer, wait for PUSH[q] >= epoch from all q
+//   C  reduce : rank r sums its own sub-slice r and the world-1 staged copies in fp32 (fixed rank
+//               order -> every rank ends up with bit-identical values), scales (1/world = the
+//               mean Horovod computes) and writes the result into sub-slice r of EVERY arena
+//      barrier 2: signal BCAST[r] = epoch on every peer, wait for BCAST[q] >= epoch from all q
+// Epochs are monotonic and live in device memory, so replaying the same captured kernel node is
+// correct.  Hazards: a rank can only enter call e+1 after every peer signalled BCAST of call e,
+// i.e. after every peer has finished reading its staging buffer and this rank's arena.
+// Spin waits are bounded (~20 s): on expiry a sticky error word is set and every later wait of this
+// rank returns at once (wrong data, but never a hung GPU); the host checks the word.
+#include <cudaTypedefs.h>
+#include <string.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ub {
+
+constexpr int PEER_MAX = UB200_MAX_PEERS;
+// signal block layout (uint32 words)
+constexpr int PF_PUSH = 0;      // [8]  written by peer q: pushes of call `epoch` have landed here
+constexpr int PF_BCAST = 8;     // [8]  written by peer q: its reduced sub-slice has landed here
+constexpr int PF_EPOCH = 16;    // local: number of completed calls
+constexpr int PF_ARRIVE_A = 17; // local: CTAs that finished phase A
+constexpr int PF_ARRIVE_C = 18; // local: CTAs that finished phase C
+constexpr int PF_ERROR = 19;    // local, sticky: (epoch << 4) | phase of the first expired wait
+constexpr int PF_WORDS = 64;
+
+struct PeerParams {
+  uint8_t* buf[PEER_MAX];
+  uint8_t* stage[PEER_MAX];
+  uint32_t* flags[PEER_MAX];
+  int rank, world;
+  long long byte_offset;   // of the slice inside the arena
+  long long nvec;          // 16-byte vectors in the slice
+  long long per;           // vectors per sub-slice (multiple of 32)
+  float scale;
+  long long timeout_cycles;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// wait until *flag >= epoch (wrap-safe); false if the wait expired or an error is already latched
+__device__ __forceinline__ bool peer_wait(uint32_t* mine, int word, uint32_t epoch, int phase,
+                                          long long timeout) {
+  if (ld_relaxed_sys(mine + PF_ERROR) != 0) return false;
+  const long long t0 = clock64();
+  int spins = 0;
+  while (static_cast<int32_t>(ld_acquire_sys(mine + word) - epoch) < 0) {
+    if ((++spins & 1023) == 0) {
+      if (clock64() - t0 > timeout || ld_relaxed_sys(mine + PF_ERROR) != 0) {
+        atomicCAS(mine + PF_ERROR, 0u, (epoch << 4) | static_cast<uint32_t>(phase));
+        return false;
+      }
+    }
+    __nanosleep(64);
+  }
+  return true;
+}
+
+template <bool kBF16>
+__device__ __forceinline__ void acc8(float (&a)[8], const uint4& v) {
+  float2 f;
+  f = Elem<kBF16>::unpack(v.x); a[0] += f.x; a[1] += f.y;
+  f = Elem<kBF16>::unpack(v.y); a[2] += f.x; a[3] += f.y;
+  f = Elem<kBF16>::unpack(v.z); a[4] += f.x; a[5] += f.y;
+  f = Elem<kBF16>::unpack(v.w); a[6] += f.x; a[7] += f.y;
+}
+
+template <bool kBF16>
+__global__ void __launch_bounds__(256, 4) peer_allreduce_kernel(const PeerParams p) {
+  uint32_t* mine = p.flags[p.rank];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp_g = blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  // every CTA reads the same value: the word is bumped by the LAST CTA of a call, after all have arrived
+  const uint32_t epoch = ld_relaxed_sys(mine + PF_EPOCH) + 1u;
+  const long long chunks = p.per >> 5;   // 32-vector (512-byte) warp chunks per sub-slice
+
+  // ------------------------------------------------------------ A: push my copy of sub-slice q to rank q
+  {
+    const uint4* src0 = reinterpret_cast<const uint4*>(p.buf[p.rank] + p.byte_offset);
+    const long long units = chunks * (p.world - 1);
+    for (long long u0 = warp_g; u0 < units; u0 += 4ll * nwarps) {
+      uint4 v[4];
+      long long dsti[4];
+      int q[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long u = u0 + static_cast<long long>(k) * nwarps;
+        dsti[k] = -1;
+        if (u < units) {
+          const long long c = u / (p.world - 1);
+          const int j = static_cast<int>(u - c * (p.world - 1));
+          q[k] = (p.rank + 1 + j) % p.world;
+          const long long vi = c * 32 + lane;               // vector inside the sub-slice
+          const long long gi = q[k] * p.per + vi;           // vector inside the slice
+          if (gi < p.nvec) {
+            v[k] = src0[gi];
+            dsti[k] = p.rank * p.per + vi;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (dsti[k] >= 0) reinterpret_cast<uint4*>(p.stage[q[k]])[dsti[k]] = v[k];
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();
+    if (atomicAdd(mine + PF_ARRIVE_A, 1u) == gridDim.x - 1) {   // last CTA of this rank: all pushes issued
+      mine[PF_ARRIVE_A] = 0;
+      __threadfence_system();
+      for (int q = 0; q < p.world; ++q) st_release_sys(p.flags[q] + PF_PUSH + p.rank, epoch);
+    }
+  }
+  if (tid < p.world) peer_wait(mine, PF_PUSH + tid, epoch, 1, p.timeout_cycles);
+  __syncthreads();
+
+  // ------------------------------------------------------------ C: reduce sub-slice `rank`, write it everywhere
+  {
+    const long long v_lo = p.rank * p.per;
+    const long long v_hi = min(p.nvec, v_lo + p.per);
+    const uint4* own = reinterpret_cast<const uint4*>(p.buf[p.rank] + p.byte_offset);
+    const uint4* stg = reinterpret_cast<const uint4*>(p.stage[p.rank]);
+    for (long long c0 = warp_g; c0 * 32 < v_hi - v_lo; c0 += 2ll * nwarps) {
+      float a[2][8];
+      long long vi[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        vi[k] = (c0 + static_cast<long long>(k) * nwarps) * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[k][i] = 0.f;
+      }
+      for (int r = 0; r < p.world; ++r) {          // fixed order 0..world-1
+        uint4 v[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          v[k] = make_uint4(0, 0, 0, 0);
+          if (v_lo + vi[k] < v_hi) v[k] = (r == p.rank) ? own[v_lo + vi[k]] : stg[r * p.per + vi[k]];
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) acc8<kBF16>(a[k], v[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (v_lo + vi[k] >= v_hi) continue;
+        uint4 o;
+        o.x = Elem<kBF16>::pack(a[k][0] * p.scale, a[k][1] * p.scale);
+        o.y = Elem<kBF16>::pack(a[k][2] * p.scale, a[k][3] * p.scale);
+        o.z = Elem<kBF16>::pack(a[k][4] * p.scale, a[k][5] * p.scale);
+        o.w = Elem<kBF16>::pack(a[k][6] * p.scale, a[k][7] * p.scale);
+        for (int j = 0; j < p.world; ++j) {
+          const int q = (p.rank + j) % p.world;
+          reinterpret_cast<uint4*>(p.buf[q] + p.byte_offset)[v_lo + vi[k]] = o;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();
+    if (atomicAdd(mine + PF_ARRIVE_C, 1u) == gridDim.x - 1) {   // last CTA: everything of this rank is out
+      mine[PF_ARRIVE_C] = 0;
+      __threadfence_system();
+      for (int q = 0; q < p.world; ++q) st_release_sys(p.flags[q] + PF_BCAST + p.rank, epoch);
+      for (int q = 0; q < p.world; ++q) peer_wait(mine, PF_BCAST + q, epoch, 2, p.timeout_cycles);
+      mine[PF_EPOCH] = epoch;
+      __threadfence_system();
+    }
+  }
+}
+
+static PFN_cuMemGetAddressRange_v3020 get_addr_range() {
+  static PFN_cuMemGetAddressRange_v3020 fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuMemGetAddressRange_v3020>(p);
+  }
+  return fn;
+}
+
+}  // namespace ub
+
+extern "C" {
+
+int64_t ub200_peer_flags_bytes(void) { return ub::PF_WORDS * 4; }
+
+int64_t ub200_peer_stage_bytes(int64_t count, int32_t world) {
+  if (count <= 0 || world < 1) return 0;
+  const int64_t nvec = (count + 7) / 8;
+  int64_t per = (nvec + world - 1) / world;
+  per = (per + 31) / 32 * 32;
+  return per * world * 16;
+}
+
+int ub200_peer_ipc_export(const void* dev_ptr, void* handle64, int64_t* offset_bytes) {
+  UB_CHECK_ARG(dev_ptr && handle64 && offset_bytes, "peer_ipc_export: null argument");
+  auto fn = ub::get_addr_range();
+  if (fn == nullptr) return ub::set_error(UB200_ECUDA, "cuMemGetAddressRange entry point unavailable");
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  CUresult r = fn(&base, &size, reinterpret_cast<CUdeviceptr>(dev_ptr));
+  if (r != CUDA_SUCCESS) return ub::set_error(UB200_ECUDA, "cuMemGetAddressRange failed (%d)", (int)r);
+  cudaIpcMemHandle_t h;
+  UB_CHECK_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  *offset_bytes = static_cast<int64_t>(reinterpret_cast<CUdeviceptr>(dev_ptr) - base);
+  return 0;
+}
+
+int ub200_peer_ipc_open(const void* handle64, void** mapped_base) {
+  UB_CHECK_ARG(handle64 && mapped_base, "peer_ipc_open: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  UB_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *mapped_base = p;
+  return 0;
+}
+
+int ub200_peer_ipc_close(void* mapped_base) {
+  UB_CHECK_ARG(mapped_base, "peer_ipc_close: null argument");
+  UB_CHECK_CUDA(cudaIpcCloseMemHandle(mapped_base));
+  return 0;
+}
+
+int ub200_peer_allreduce(const ub200_peer_allreduce_args* a, ub200_stream_t stream) {
+  UB_CHECK_ARG(a, "peer_allreduce: null args");
+  UB_CHECK_ARG(a->world >= 1 && a->world <= UB200_MAX_PEERS && a->rank >= 0 && a->rank < a->world,
+               "peer_allreduce: rank %d / world %d", a->rank, a->world);
+  UB_CHECK_ARG(a->dtype == UB200_F16 || a->dtype == UB200_BF16, "peer_allreduce: dtype");
+  UB_CHECK_ARG(a->offset >= 0 && a->count >= 0 && a->offset % 8 == 0 && a->count % 8 == 0,
+               "peer_allreduce: offset / count must be multiples of 8 elements (16 bytes)");
+  if (a->count == 0) return 0;
+  ub::PeerParams p{};
+  for (int q = 0; q < a->world; ++q) {
+    UB_CHECK_ARG(a->buf[q] && a->stage[q] && a->flags[q], "peer_allreduce: null pointer for rank %d", q);
+    UB_CHECK_ARG((reinterpret_cast<uintptr_t>(a->buf[q]) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(a->stage[q]) & 15) == 0,
+                 "peer_allreduce: buffers must be 16-byte aligned");
+    p.buf[q] = static_cast<uint8_t*>(a->buf[q]);
+    p.stage[q] = static_cast<uint8_t*>(a->stage[q]);
+    p.flags[q] = a->flags[q];
+  }
+  p.rank = a->rank;
+  p.world = a->world;
+  p.byte_offset = a->offset * 2;
+  p.nvec = a->count / 8;
+  long long per = (p.nvec + a->world - 1) / a->world;
+  per = (per + 31) / 32 * 32;
+  p.per = per;
+  UB_CHECK_ARG(per * a->world * 16 <= a->stage_bytes,
+               "peer_allreduce: staging buffer too small (%lld < %lld bytes)", (long long)a->stage_bytes,
+               (long long)(per * a->world * 16));
+  p.scale = a->scale;
+  p.timeout_cycles = a->timeout_ms > 0 ? static_cast<long long>(a->timeout_ms) * 1900000ll : 38000000000ll;
+  int ctas = a->max_ctas > 0 ? a->max_ctas : 32;
+  const long long chunks = per / 32;
+  const long long want = (chunks * (a->world > 1 ? a->world - 1 : 1) + 7) / 8;   // >= 1 warp-round per CTA
+  if (ctas > want) ctas = static_cast<int>(want < 1 ? 1 : want);
+  if (ctas > ub::num_sms()) ctas = ub::num_sms();
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  ub::ProfScope prof(s);
+  if (a->dtype == UB200_BF16)
+    ub::peer_allreduce_kernel<true><<<ctas, 256, 0, s>>>(p);
+  else
+    ub::peer_allreduce_kernel<false><<<ctas, 256, 0, s>>>(p);
+  UB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

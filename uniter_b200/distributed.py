@@ -40,6 +40,100 @@ def _capped_nccl_group(max_ctas):
         return None
 
 
+class PeerExchange(object):
+    """All-reduce (mean) of slices of one flat 16-bit buffer over NVLink peer memory, without NCCL:
+    the kernel of csrc/peer.cu (ub200_peer_allreduce).  Construction is collective: every rank maps
+    every other rank's buffer, staging buffer and signal block with cudaIpc (handles travel through
+    torch.distributed's object all-gather).  `all_reduce(lo, hi)` only enqueues ONE kernel on the
+    current stream — no host synchronisation, capturable in a CUDA graph; every rank must issue the
+    same sequence of calls.  Replaces hvd.allreduce_ of utils/distributed.py:16-43."""
+
+    def __init__(self, flat, group=None, max_count=None, timeout_ms=0):
+        import ctypes as C
+        from . import _lib
+        self.lib = _lib.load()
+        self.flat = flat
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if self.world > _lib.MAX_PEERS:
+            raise RuntimeError("PeerExchange supports up to %d ranks of one NVSwitch domain" % _lib.MAX_PEERS)
+        self.dtype = _lib.dtype_code(flat.dtype)
+        self.timeout_ms = int(timeout_ms)
+        n = int(max_count or flat.numel())
+        self.stage_bytes = int(self.lib.ub200_peer_stage_bytes(n, self.world))
+        fb = int(self.lib.ub200_peer_flags_bytes())
+        # one allocation per rank: [staging | signal block]; large enough to be its own cudaMalloc
+        # segment of the caching allocator (an allocation can be opened once per process)
+        self.ws = torch.zeros(max(self.stage_bytes, 32 << 20) + fb, dtype=torch.uint8, device=flat.device)
+        self._flags_off = self.ws.numel() - fb
+        torch.cuda.synchronize(flat.device)
+
+        def export(t):
+            h = (C.c_char * 64)()
+            off = C.c_int64(0)
+            _lib.check(self.lib.ub200_peer_ipc_export(C.c_void_p(t.data_ptr()), h, C.byref(off)))
+            return bytes(h.raw), int(off.value)
+
+        mine = (export(flat), export(self.ws))
+        if mine[0][0] == mine[1][0]:
+            raise RuntimeError("PeerExchange: the buffer and the workspace share one allocation")
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        self._mapped = []
+        self.buf, self.stage, self.flags = [], [], []
+        for q, ((hb, ob), (hw, ow)) in enumerate(everyone):
+            if q == self.rank:
+                b, w = flat.data_ptr(), self.ws.data_ptr()
+            else:
+                pb, pw = C.c_void_p(), C.c_void_p()
+                _lib.check(self.lib.ub200_peer_ipc_open(hb, C.byref(pb)))
+                _lib.check(self.lib.ub200_peer_ipc_open(hw, C.byref(pw)))
+                self._mapped += [pb.value, pw.value]
+                b, w = pb.value + ob, pw.value + ow
+            self.buf.append(b)
+            self.stage.append(w)
+            self.flags.append(w + self._flags_off)
+        self._args = {}
+        self.calls = 0
+        dist.barrier(group=group)          # every signal block is zeroed and mapped before the first kernel
+
+    def _make(self, lo, hi, max_ctas):
+        import ctypes as C
+        from . import _lib
+        a = _lib.PeerAllreduceArgs()
+        for q in range(self.world):
+            a.buf[q], a.stage[q] = self.buf[q], self.stage[q]
+            a.flags[q] = C.cast(C.c_void_p(self.flags[q]), C.POINTER(C.c_uint32))
+        a.rank, a.world = self.rank, self.world
+        a.offset, a.count = lo, hi - lo
+        a.stage_bytes = self.stage_bytes
+        a.dtype, a.max_ctas = self.dtype, int(max_ctas)
+        a.scale = 1.0 / self.world
+        a.timeout_ms = self.timeout_ms
+        return a
+
+    def all_reduce(self, lo, hi, max_ctas=32):
+        """flat[lo:hi] <- mean over ranks, in place, on the current stream (lo, hi multiples of 8)."""
+        from . import _lib
+        key = (lo, hi, max_ctas)
+        a = self._args.get(key)
+        if a is None:
+            a = self._args[key] = self._make(lo, hi, max_ctas)
+        _lib.check(self.lib.ub200_peer_allreduce(a, _lib.current_stream()))
+        self.calls += 1
+
+    def error_word(self):
+        """0, or (call number << 4 | phase) of the first flag wait that expired on this rank (host read)."""
+        w = self.ws[self._flags_off:].view(torch.int32)
+        return int(w[19].item())
+
+    def close(self):
+        for p in self._mapped:
+            self.lib.ub200_peer_ipc_close(p)
+        self._mapped = []
+
+
 def broadcast_parameters(model, root=0):
     """Rank `root`'s parameters and buffers -> every rank (startup only)."""
     works = []
@@ -56,14 +150,19 @@ def broadcast_parameters(model, root=0):
 class GradientReducer:
     """Average gradients over ranks: in-place all-reduce of slices of the model's gradient arena."""
 
-    def __init__(self, model, overlap_chunks=4, sm_reserve=0):
+    def __init__(self, model, overlap_chunks=4, sm_reserve=0, transport="nccl", peer_ctas=32,
+                 peer_tail_ctas=64):
         """`overlap_chunks` > 1: the encoder layers are all-reduced in that many groups (top group
         first, together with the task-head / pooler slice, which is final by then) while the backward
         of the earlier layers still runs; only the embedding front-end slice is reduced after the
         backward.  `sm_reserve` > 0: during that overlap the library's persistent kernels leave
         `sm_reserve` SMs to the collective, and the collective runs on a communicator capped to the
         same number of CTAs (must be called by all ranks).  Measured on 2 x B200 (C2,
-        profiles/r01_scale2_variants.json): reserving SMs cost more than it saved, hence default 0."""
+        profiles/r01_scale2_variants.json): reserving SMs cost more than it saved, hence default 0.
+        `transport` "peer": the slices are exchanged by the library's own NVLink peer-memory kernel
+        (PeerExchange; `peer_ctas` CTAs while the backward runs, `peer_tail_ctas` for the slices
+        shipped after it) instead of NCCL — no host involvement, so the whole step including the
+        exchange is one CUDA graph."""
         self.model = model
         self.arena = GradArena.attach(model)
         self.encoders = self.arena.encoders
@@ -76,12 +175,24 @@ class GradientReducer:
             from . import _lib
             self._lib = _lib.load()
         self.overlap_chunks = overlap_chunks
+        self.transport = transport
+        self.peer = None
+        self.peer_ctas, self.peer_tail_ctas = int(peer_ctas), int(peer_tail_ctas)
+        if transport == "peer":
+            if not (nccl and self.arena.flat.is_cuda):
+                raise RuntimeError("transport='peer' needs an initialised NCCL process group on CUDA devices")
+            self.peer = PeerExchange(self.arena.flat)
         self._pending = []
         self._done = []               # element ranges of the arena already shipped in this step
         # created up front: the first use may be inside a CUDA-graph capture
-        self._comm_stream = torch.cuda.Stream() if self.arena.flat.is_cuda else None
+        # (peer transport: high priority, so that the exchange CTAs are placed as soon as an SM has room
+        #  instead of queueing behind the next persistent GEMM launch)
+        self._comm_stream = (torch.cuda.Stream(priority=-1 if transport == "peer" else 0)
+                             if self.arena.flat.is_cuda else None)
         self._reserved = False
         self._bwd_seen = {}
+        self._tail = False             # shipping what is left after the backward (nothing to overlap)
+        self._peer_inflight = False
         # GraphedStep (split mode) sets this while it CAPTURES a step: instead of issuing NCCL, the
         # reducer reports which arena ranges become final at this point of the backward
         self._split_cb = None
@@ -114,7 +225,11 @@ class GradientReducer:
             self._reserved = True
         with torch.cuda.stream(self._comm_stream):
             self._comm_stream.wait_event(ev)
-            self._pending.append(_avg_all_reduce(self.arena.flat[lo:hi], async_op=True, group=self._group))
+            if self.peer is not None:
+                self.peer.all_reduce(lo, hi, self.peer_tail_ctas if self._tail else self.peer_ctas)
+                self._peer_inflight = True
+            else:
+                self._pending.append(_avg_all_reduce(self.arena.flat[lo:hi], async_op=True, group=self._group))
         self._done.append((lo, hi))
 
     def _on_chunk(self, enc, lo, hi):
@@ -160,11 +275,18 @@ class GradientReducer:
         works = self._pending
         self._pending = []
         cuda = self.arena.flat.is_cuda
-        for lo, hi in rest:
-            if cuda and self._comm_stream is not None and self._done:
-                self._ship(lo, hi)
-            else:
-                works.append(_avg_all_reduce(self.arena.flat[lo:hi], async_op=cuda, group=self._group))
+        self._tail = True
+        try:
+            for lo, hi in rest:
+                if cuda and self._comm_stream is not None and (self._done or self.peer is not None):
+                    self._ship(lo, hi)
+                else:
+                    works.append(_avg_all_reduce(self.arena.flat[lo:hi], async_op=cuda, group=self._group))
+        finally:
+            self._tail = False
+        if self._peer_inflight:           # join: the current stream continues after the last exchange kernel
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+            self._peer_inflight = False
         works += self._pending
         self._pending = []
         self._done = []
