@@ -110,30 +110,35 @@ __global__ void __launch_bounds__(256, 4) peer_allreduce_kernel(const PeerParams
   // ------------------------------------------------------------ A: push my copy of sub-slice q to rank q
   {
     const uint4* src0 = reinterpret_cast<const uint4*>(p.buf[p.rank] + p.byte_offset);
-    const long long units = chunks * (p.world - 1);
-    for (long long u0 = warp_g; u0 < units; u0 += 4ll * nwarps) {
+    // 32-bit index arithmetic: a slice has < 2^31 vectors (ub200_peer_allreduce checks)
+    const uint32_t wm1 = static_cast<uint32_t>(p.world - 1);
+    const uint32_t units = static_cast<uint32_t>(chunks) * wm1;
+    const uint32_t per = static_cast<uint32_t>(p.per), nvec = static_cast<uint32_t>(p.nvec);
+    for (uint32_t u0 = warp_g; u0 < units; u0 += 4u * nwarps) {
       uint4 v[4];
-      long long dsti[4];
+      uint32_t dsti[4];
       int q[4];
+      bool on[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const long long u = u0 + static_cast<long long>(k) * nwarps;
-        dsti[k] = -1;
-        if (u < units) {
-          const long long c = u / (p.world - 1);
-          const int j = static_cast<int>(u - c * (p.world - 1));
-          q[k] = (p.rank + 1 + j) % p.world;
-          const long long vi = c * 32 + lane;               // vector inside the sub-slice
-          const long long gi = q[k] * p.per + vi;           // vector inside the slice
-          if (gi < p.nvec) {
+        const uint32_t u = u0 + static_cast<uint32_t>(k) * nwarps;
+        on[k] = false;
+        if (u < units && u >= u0) {
+          const uint32_t c = u / wm1;
+          const uint32_t j = u - c * wm1;
+          q[k] = static_cast<int>((p.rank + 1 + j) % p.world);
+          const uint32_t vi = c * 32 + lane;                // vector inside the sub-slice
+          const uint32_t gi = q[k] * per + vi;              // vector inside the slice
+          if (gi < nvec) {
             v[k] = src0[gi];
-            dsti[k] = p.rank * p.per + vi;
+            dsti[k] = p.rank * per + vi;
+            on[k] = true;
           }
         }
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (dsti[k] >= 0) reinterpret_cast<uint4*>(p.stage[q[k]])[dsti[k]] = v[k];
+        if (on[k]) reinterpret_cast<uint4*>(p.stage[q[k]])[dsti[k]] = v[k];
     }
   }
   __syncthreads();
@@ -285,6 +290,7 @@ int ub200_peer_allreduce(const ub200_peer_allreduce_args* a, ub200_stream_t stre
   long long per = (p.nvec + a->world - 1) / a->world;
   per = (per + 31) / 32 * 32;
   p.per = per;
+  UB_CHECK_ARG(per * a->world < (1ll << 31), "peer_allreduce: slice too large (%lld vectors)", (long long)p.nvec);
   UB_CHECK_ARG(per * a->world * 16 <= a->stage_bytes,
                "peer_allreduce: staging buffer too small (%lld < %lld bytes)", (long long)a->stage_bytes,
                (long long)(per * a->world * 16));
