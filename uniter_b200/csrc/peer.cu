@@ -207,6 +207,114 @@ __global__ void __launch_bounds__(256, 4) peer_allreduce_kernel(const PeerParams
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Form 2 (max_ctas == 0): the same protocol as TWO kernels of many short-lived CTAs.
+// A persistent exchange CTA holds 16 K registers of its SM for the whole exchange: while it is there,
+// the register-hungry row kernels of the backward (LayerNorm backward: 61 K registers per CTA,
+// attention backward: 2 x 32 K) cannot be placed on that SM, and the chain the exchange is supposed to
+// hide behind slows down.  Here every CTA moves 32 KB (push) / 8 KB (reduce) and exits, the grids are
+// sized by the work, and the stream they run on has a LOWER priority than the backward's stream:
+// the block scheduler places the backward's CTAs first and the exchange fills what is left — next to
+// the persistent GEMM CTAs (80-96 registers x 512 threads leave room for exactly one 16 K-register CTA).
+//   peer_push_kernel    grid (per / 2048, world - 1): block (x, y) copies vectors [2048 x, 2048 (x + 1)) of
+//                       sub-slice q = rank + 1 + y into stage_q[rank]; destinations rotate with the rank so
+//                       that no rank's ingress sees all senders at once.  Last CTA: PUSH signals.
+//   peer_reduce_kernel  grid (per / 512): waits for every PUSH signal, reduces 512 vectors of sub-slice
+//                       `rank`, writes them into every arena.  Last CTA: BCAST signals, waits for the
+//                       peers' BCAST signals, bumps the epoch.
+constexpr int PUSH_U = 8, PUSH_VPC = 256 * PUSH_U;      // vectors per push CTA
+constexpr int RED_U = 2, RED_VPC = 256 * RED_U;          // vectors per reduce CTA
+
+__global__ void __launch_bounds__(256, 4) peer_push_kernel(const PeerParams p) {
+  uint32_t* mine = p.flags[p.rank];
+  const uint32_t epoch = ld_relaxed_sys(mine + PF_EPOCH) + 1u;
+  const int q = (p.rank + 1 + static_cast<int>(blockIdx.y)) % p.world;
+  const uint32_t per = static_cast<uint32_t>(p.per), nvec = static_cast<uint32_t>(p.nvec);
+  const uint32_t v0 = blockIdx.x * PUSH_VPC + threadIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(p.buf[p.rank] + p.byte_offset) + static_cast<size_t>(q) * per;
+  uint4* dst = reinterpret_cast<uint4*>(p.stage[q]) + static_cast<size_t>(p.rank) * per;
+  const uint32_t q_len = (static_cast<uint32_t>(q) * per < nvec) ? min(per, nvec - q * per) : 0u;
+  uint4 v[PUSH_U];
+#pragma unroll
+  for (int k = 0; k < PUSH_U; ++k) {
+    const uint32_t vi = v0 + k * 256;
+    if (vi < q_len) v[k] = src[vi];
+  }
+#pragma unroll
+  for (int k = 0; k < PUSH_U; ++k) {
+    const uint32_t vi = v0 + k * 256;
+    if (vi < q_len) dst[vi] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const uint32_t total = gridDim.x * gridDim.y;
+    if (atomicAdd(mine + PF_ARRIVE_A, 1u) == total - 1) {
+      mine[PF_ARRIVE_A] = 0;
+      __threadfence_system();
+      for (int r = 0; r < p.world; ++r) st_release_sys(p.flags[r] + PF_PUSH + p.rank, epoch);
+    }
+  }
+}
+
+template <bool kBF16>
+__global__ void __launch_bounds__(256, 4) peer_reduce_kernel(const PeerParams p) {
+  uint32_t* mine = p.flags[p.rank];
+  const int tid = threadIdx.x;
+  const uint32_t epoch = ld_relaxed_sys(mine + PF_EPOCH) + 1u;
+  // (this rank's own pushes are complete by stream order: the push kernel precedes this one)
+  if (tid < p.world && tid != p.rank) peer_wait(mine, PF_PUSH + tid, epoch, 1, p.timeout_cycles);
+  __syncthreads();
+  const uint32_t per = static_cast<uint32_t>(p.per), nvec = static_cast<uint32_t>(p.nvec);
+  const uint32_t v_lo = static_cast<uint32_t>(p.rank) * per;
+  const uint32_t len = (v_lo < nvec) ? min(per, nvec - v_lo) : 0u;
+  const uint4* own = reinterpret_cast<const uint4*>(p.buf[p.rank] + p.byte_offset) + v_lo;
+  const uint4* stg = reinterpret_cast<const uint4*>(p.stage[p.rank]);
+  float a[RED_U][8];
+  uint32_t vi[RED_U];
+#pragma unroll
+  for (int k = 0; k < RED_U; ++k) {
+    vi[k] = blockIdx.x * RED_VPC + k * 256 + tid;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[k][i] = 0.f;
+  }
+  for (int r = 0; r < p.world; ++r) {          // fixed order 0..world-1: bit-identical on every rank
+    uint4 v[RED_U];
+#pragma unroll
+    for (int k = 0; k < RED_U; ++k) {
+      v[k] = make_uint4(0, 0, 0, 0);
+      if (vi[k] < len) v[k] = (r == p.rank) ? own[vi[k]] : __ldcg(stg + static_cast<size_t>(r) * per + vi[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < RED_U; ++k) acc8<kBF16>(a[k], v[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < RED_U; ++k) {
+    if (vi[k] >= len) continue;
+    uint4 o;
+    o.x = Elem<kBF16>::pack(a[k][0] * p.scale, a[k][1] * p.scale);
+    o.y = Elem<kBF16>::pack(a[k][2] * p.scale, a[k][3] * p.scale);
+    o.z = Elem<kBF16>::pack(a[k][4] * p.scale, a[k][5] * p.scale);
+    o.w = Elem<kBF16>::pack(a[k][6] * p.scale, a[k][7] * p.scale);
+    for (int j = 0; j < p.world; ++j) {
+      const int q = (p.rank + j) % p.world;
+      reinterpret_cast<uint4*>(p.buf[q] + p.byte_offset)[v_lo + vi[k]] = o;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();
+    if (atomicAdd(mine + PF_ARRIVE_C, 1u) == gridDim.x - 1) {
+      mine[PF_ARRIVE_C] = 0;
+      __threadfence_system();
+      for (int q = 0; q < p.world; ++q) st_release_sys(p.flags[q] + PF_BCAST + p.rank, epoch);
+      for (int q = 0; q < p.world; ++q) peer_wait(mine, PF_BCAST + q, epoch, 2, p.timeout_cycles);
+      mine[PF_EPOCH] = epoch;
+      __threadfence_system();
+    }
+  }
+}
+
 static PFN_cuMemGetAddressRange_v3020 get_addr_range() {
   static PFN_cuMemGetAddressRange_v3020 fn = nullptr;
   if (fn == nullptr) {
@@ -229,7 +337,7 @@ int64_t ub200_peer_stage_bytes(int64_t count, int32_t world) {
   if (count <= 0 || world < 1) return 0;
   const int64_t nvec = (count + 7) / 8;
   int64_t per = (nvec + world - 1) / world;
-  per = (per + 31) / 32 * 32;
+  per = (per + ub::PUSH_VPC - 1) / ub::PUSH_VPC * ub::PUSH_VPC;
   return per * world * 16;
 }
 
@@ -288,7 +396,7 @@ int ub200_peer_allreduce(const ub200_peer_allreduce_args* a, ub200_stream_t stre
   p.byte_offset = a->offset * 2;
   p.nvec = a->count / 8;
   long long per = (p.nvec + a->world - 1) / a->world;
-  per = (per + 31) / 32 * 32;
+  per = (per + ub::PUSH_VPC - 1) / ub::PUSH_VPC * ub::PUSH_VPC;   // whole push CTAs (and whole warp chunks)
   p.per = per;
   UB_CHECK_ARG(per * a->world < (1ll << 31), "peer_allreduce: slice too large (%lld vectors)", (long long)p.nvec);
   UB_CHECK_ARG(per * a->world * 16 <= a->stage_bytes,
@@ -296,12 +404,32 @@ int ub200_peer_allreduce(const ub200_peer_allreduce_args* a, ub200_stream_t stre
                (long long)(per * a->world * 16));
   p.scale = a->scale;
   p.timeout_cycles = a->timeout_ms > 0 ? static_cast<long long>(a->timeout_ms) * 1900000ll : 38000000000ll;
-  int ctas = a->max_ctas > 0 ? a->max_ctas : 32;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a->max_ctas <= 0) {
+    // form 2: work-sized grids of short-lived CTAs (push kernel, then reduce kernel)
+    if (a->world > 1) {
+      ub::ProfScope prof(s);
+      ub::peer_push_kernel<<<dim3(static_cast<unsigned>(per / ub::PUSH_VPC), a->world - 1), 256, 0, s>>>(p);
+      UB_CHECK_CUDA(cudaGetLastError());
+    }
+    const long long v_lo = p.rank * per;
+    long long len = p.nvec - v_lo;
+    if (len > per) len = per;
+    if (len < 0) len = 0;
+    const unsigned gc = static_cast<unsigned>((len + ub::RED_VPC - 1) / ub::RED_VPC);
+    ub::ProfScope prof(s);
+    if (a->dtype == UB200_BF16)
+      ub::peer_reduce_kernel<true><<<gc < 1 ? 1 : gc, 256, 0, s>>>(p);
+    else
+      ub::peer_reduce_kernel<false><<<gc < 1 ? 1 : gc, 256, 0, s>>>(p);
+    UB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  int ctas = a->max_ctas;
   const long long chunks = per / 32;
   const long long want = (chunks * (a->world > 1 ? a->world - 1 : 1) + 7) / 8;   // >= 1 warp-round per CTA
   if (ctas > want) ctas = static_cast<int>(want < 1 ? 1 : want);
   if (ctas > ub::num_sms()) ctas = ub::num_sms();
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   ub::ProfScope prof(s);
   if (a->dtype == UB200_BF16)
     ub::peer_allreduce_kernel<true><<<ctas, 256, 0, s>>>(p);

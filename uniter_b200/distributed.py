@@ -113,8 +113,10 @@ class PeerExchange(object):
         a.timeout_ms = self.timeout_ms
         return a
 
-    def all_reduce(self, lo, hi, max_ctas=32):
-        """flat[lo:hi] <- mean over ranks, in place, on the current stream (lo, hi multiples of 8)."""
+    def all_reduce(self, lo, hi, max_ctas=0):
+        """flat[lo:hi] <- mean over ranks, in place, on the current stream (lo, hi multiples of 8).
+        max_ctas 0: a push kernel + a reduce kernel of short-lived CTAs sized by the work (the form that
+        yields SMs to the backward it overlaps); > 0: one persistent kernel of that many CTAs."""
         from . import _lib
         key = (lo, hi, max_ctas)
         a = self._args.get(key)
@@ -150,8 +152,8 @@ def broadcast_parameters(model, root=0):
 class GradientReducer:
     """Average gradients over ranks: in-place all-reduce of slices of the model's gradient arena."""
 
-    def __init__(self, model, overlap_chunks=4, sm_reserve=0, transport="nccl", peer_ctas=32,
-                 peer_tail_ctas=64):
+    def __init__(self, model, overlap_chunks=4, sm_reserve=0, transport="nccl", peer_ctas=0,
+                 peer_tail_ctas=0):
         """`overlap_chunks` > 1: the encoder layers are all-reduced in that many groups (top group
         first, together with the task-head / pooler slice, which is final by then) while the backward
         of the earlier layers still runs; only the embedding front-end slice is reduced after the
@@ -160,8 +162,9 @@ class GradientReducer:
         same number of CTAs (must be called by all ranks).  Measured on 2 x B200 (C2,
         profiles/r01_scale2_variants.json): reserving SMs cost more than it saved, hence default 0.
         `transport` "peer": the slices are exchanged by the library's own NVLink peer-memory kernel
-        (PeerExchange; `peer_ctas` CTAs while the backward runs, `peer_tail_ctas` for the slices
-        shipped after it) instead of NCCL — no host involvement, so the whole step including the
+        (PeerExchange; `peer_ctas` / `peer_tail_ctas`: 0 = work-sized grids of short-lived CTAs, > 0 =
+        one persistent kernel of that many CTAs, for the slices shipped while the backward runs / after
+        it) instead of NCCL — no host involvement, so the whole step including the
         exchange is one CUDA graph."""
         self.model = model
         self.arena = GradArena.attach(model)
@@ -185,10 +188,9 @@ class GradientReducer:
         self._pending = []
         self._done = []               # element ranges of the arena already shipped in this step
         # created up front: the first use may be inside a CUDA-graph capture
-        # (peer transport: high priority, so that the exchange CTAs are placed as soon as an SM has room
-        #  instead of queueing behind the next persistent GEMM launch)
-        self._comm_stream = (torch.cuda.Stream(priority=-1 if transport == "peer" else 0)
-                             if self.arena.flat.is_cuda else None)
+        # (lowest priority: GraphedStep captures the step itself on a high-priority stream, so the block
+        #  scheduler places the backward's CTAs first and the exchange's CTAs fill what is left)
+        self._comm_stream = torch.cuda.Stream(priority=0) if self.arena.flat.is_cuda else None
         self._reserved = False
         self._bwd_seen = {}
         self._tail = False             # shipping what is left after the backward (nothing to overlap)

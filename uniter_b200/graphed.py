@@ -71,6 +71,9 @@ class GraphedStep(object):
         self.buckets = {}
         self.pool = None
         self.rng_counter = torch.zeros(1, device=self.device, dtype=torch.int64)
+        # the step is captured on a HIGH-priority stream: kernel nodes inherit it, side-stream work forked
+        # inside the step (the reducer's gradient exchange, priority 0) yields SMs to the step's own kernels
+        self._cap_stream = torch.cuda.Stream(device=self.device, priority=-1)
         self._meta_pinned = {}
         self.captures = 0
 
@@ -137,8 +140,14 @@ class GraphedStep(object):
         # (the warm-up runs are REAL steps: an accumulating step would add its gradients several times
         #  and an optimizer would move the weights, so the arena is restored and the optimizer only
         #  prepares its device tables)
+        # A capture must be a purely LOCAL event: ranks see different batches, so they meet new buckets
+        # (new shapes of the padded masked-token lists, new token counts) at different steps and in
+        # different numbers.  The warm-up therefore runs WITHOUT the reducer — a warm-up step that
+        # all-reduced would be a collective the other ranks do not take part in (NCCL: hang; peer
+        # exchange: ranks pair up different calls) — and the capture itself executes nothing.
         saved = self.arena.flat.clone() if accumulate else None
         opt, self.optimizer = self.optimizer, None
+        red, self.reducer = self.reducer, None
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -148,6 +157,7 @@ class GraphedStep(object):
                 self.arena.flat.copy_(saved)
         torch.cuda.current_stream().wait_stream(s)
         self.optimizer = opt
+        self.reducer = red
         if opt is not None:
             opt.prepare()
         if self.pool is None:
@@ -160,7 +170,7 @@ class GraphedStep(object):
             self._capture_split(bk, accumulate, tag)
         else:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=self.pool):
+            with torch.cuda.graph(g, pool=self.pool, stream=self._cap_stream):
                 bk.loss = self._run(bk, accumulate, tag)
             bk.graphs, bk.ship_after = [g], [[]]
         bk.launches = int(lib.ub200_launch_count() - n0)     # libub200 kernels inside one replay
