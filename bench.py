@@ -70,10 +70,11 @@ def parse():
                          "captured as one graph per layer group and each group's slice is all-reduced (eagerly, on a "
                          "side stream) while the next group's graph runs; 'in-graph' = NCCL captured inside the graph "
                          "(hangs with this torch / NCCL build: measured, kept for experiments only)")
-    ap.add_argument("--peer-ctas", type=int, default=0,
-                    help="--allreduce peer: exchange kernels that overlap the backward: 0 = push + reduce kernels of "
-                         "short-lived CTAs sized by the work, N > 0 = one persistent kernel of N CTAs")
-    ap.add_argument("--peer-tail-ctas", type=int, default=0,
+    ap.add_argument("--peer-ctas", type=int, default=-1,
+                    help="--allreduce peer: form of the exchange that overlaps the backward: -1 = copy engines move the "
+                         "bytes, SMs only reduce locally; 0 = push + reduce kernels of short-lived CTAs; N > 0 = one "
+                         "persistent kernel of N CTAs")
+    ap.add_argument("--peer-tail-ctas", type=int, default=-1,
                     help="--allreduce peer: the same for the exchange kernels issued after the backward")
     ap.add_argument("--token-bucket", type=int, default=128,
                     help="graph mode: token counts are padded to a multiple of this with a dummy sequence")
@@ -705,10 +706,16 @@ def main():
     for i in range(n_host):
         task = tasks[i % len(tasks)]
         if i < len(tasks):
-            # the canonical batch of the config (seed 1234 -> T = 3451 on rank 0)
+            # the canonical batch of the config (seed 1234 -> T = 3451).  Weak scaling means
+            # the SAME work on every GPU: every rank uses the canonical LENGTH profile (so no rank is the
+            # straggler of the synchronous step just because it drew longer sequences) with its own token
+            # ids / region features / masks.
             b = synth_batch(CF["B"], CF["tl"][0], CF["tl"][1], CF["nbb"][0], CF["nbb"][1],
-                            CF["seed"] + 1000 * rank, mlm_prob=CF["mlm_prob"])
+                            CF["seed"], mlm_prob=CF["mlm_prob"])
             canon = (b["txt_lens"], b["num_bbs"])
+            if rank > 0:
+                b = synth_batch(CF["B"], 0, 0, 0, 0, CF["seed"] + 1000 * rank,
+                                txt_lens=canon[0], num_bbs=canon[1], mlm_prob=CF["mlm_prob"])
         else:
             # further host batches of the rotation: the SAME length profile (so that the e2e leg does
             # the same work per step as the resident leg) with different token ids / features / masks
@@ -998,7 +1005,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
             "config": {"workload": "%s: %s %d-layer encoder fwd+bwd + %s, "
-                                   "B=%d per GPU, varlen S~54 (rank-0 batch: T=%d valid tokens, max S=%d), "
+                                   "B=%d per GPU, varlen S~54 (every rank: T=%d valid tokens, max S=%d; own ids / features / masks), "
                                    "train mode dropout 0.1"
                                    % (CF["label"], CF["arch_name"], NL,
                                       "MLM head (15% text masked)" if tasks == ("mlm",) else

@@ -43,7 +43,7 @@ def main():
         worst = 0.0
         for lo, hi in [(0, 8), (8, 272), (1024, 1024 + 8 * 4097), (0, 1 << 20), (40, n), (0, n)]:
             hi = min(hi, n)
-            for rep in range(2):
+            for rep in range(3):
                 src = torch.randn(hi - lo, device=dev, generator=g) * (1.0 + rank)
                 flat[lo:hi] = src.to(dtype)
                 before = flat.clone()
@@ -51,7 +51,7 @@ def main():
                 dist.all_reduce(want, op=dist.ReduceOp.SUM)
                 want = (want * (1.0 / world)).to(dtype)
                 dist.barrier()
-                px.all_reduce(lo, hi, max_ctas=0 if rep == 0 else 7)    # both kernel forms
+                px.all_reduce(lo, hi, max_ctas=(-1, 0, 7)[rep])    # the three forms: copy engines / short-lived CTAs / persistent
                 torch.cuda.synchronize()
                 got = flat[lo:hi]
                 # two ranks: a + b is order independent -> bit exact; more ranks: NCCL's fp32 summation
@@ -98,7 +98,7 @@ def main():
             # ---- timing
             times = {}
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            for ctas in (0, 32, 64, 148):        # 0 = push + reduce kernels of short-lived CTAs
+            for ctas in (-1, 0, 148):        # copy engines / short-lived CTAs / persistent
                 for _ in range(3):
                     px.all_reduce(0, n, max_ctas=ctas)
                 dist.barrier()
@@ -108,7 +108,7 @@ def main():
                     px.all_reduce(0, n, max_ctas=ctas)
                 e1.record()
                 torch.cuda.synchronize()
-                times["peer_%d_ctas" % ctas] = e0.elapsed_time(e1) / 10
+                times["peer_form_%d" % ctas] = e0.elapsed_time(e1) / 10
             for _ in range(3):
                 dist.all_reduce(flat, op=dist.ReduceOp.AVG)
             dist.barrier()

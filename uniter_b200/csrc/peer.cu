@@ -315,6 +315,75 @@ __global__ void __launch_bounds__(256, 4) peer_reduce_kernel(const PeerParams p)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Form 3 (max_ctas < 0), the default: the COPY ENGINES move the bytes, the SMs only reduce.
+// Measured on 2 x B200 (profiles/r02_k_*): with either SM form the step takes the same 4.15 ms whether
+// the exchange is issued slice by slice during the backward or once after it — exchange CTAs that are
+// scheduled ahead of the backward's CTAs stall it, exchange CTAs scheduled behind them do not run
+// until it is over.  So the SMs are taken out of the data path:
+//   A  (world-1) cudaMemcpyAsync nodes: my sub-slice q  ->  stage_q[rank]          (DMA over NVLink)
+//      peer_sync_kernel<1>  (1 CTA, 32 threads): PUSH signals / waits
+//   C  peer_reduce_local_kernel: own sub-slice + staged copies -> own arena          (local HBM only)
+//      (world-1) cudaMemcpyAsync nodes: reduced sub-slice -> every peer's arena     (DMA over NVLink)
+//      peer_sync_kernel<2>: BCAST signals / waits, epoch bump
+// Same protocol, same flags, same hazards as above; every node is capturable, so the exchange is still
+// part of the step's one CUDA graph, and it shares nothing with the backward but HBM bandwidth.
+template <int kPhase>
+__global__ void __launch_bounds__(32) peer_sync_kernel(const PeerParams p) {
+  uint32_t* mine = p.flags[p.rank];
+  const int tid = threadIdx.x;
+  const uint32_t epoch = ld_relaxed_sys(mine + PF_EPOCH) + 1u;
+  const int word = (kPhase == 1) ? PF_PUSH : PF_BCAST;
+  if (tid < p.world) {
+    __threadfence_system();
+    st_release_sys(p.flags[tid] + word + p.rank, epoch);
+    peer_wait(mine, word + tid, epoch, kPhase, p.timeout_cycles);
+  }
+  __syncwarp();
+  if (kPhase == 2 && tid == 0) {
+    mine[PF_EPOCH] = epoch;
+    __threadfence_system();
+  }
+}
+
+template <bool kBF16>
+__global__ void __launch_bounds__(256, 4) peer_reduce_local_kernel(const PeerParams p) {
+  const int tid = threadIdx.x;
+  const uint32_t per = static_cast<uint32_t>(p.per), nvec = static_cast<uint32_t>(p.nvec);
+  const uint32_t v_lo = static_cast<uint32_t>(p.rank) * per;
+  const uint32_t len = (v_lo < nvec) ? min(per, nvec - v_lo) : 0u;
+  uint4* own = reinterpret_cast<uint4*>(p.buf[p.rank] + p.byte_offset) + v_lo;
+  const uint4* stg = reinterpret_cast<const uint4*>(p.stage[p.rank]);
+  float a[RED_U][8];
+  uint32_t vi[RED_U];
+#pragma unroll
+  for (int k = 0; k < RED_U; ++k) {
+    vi[k] = blockIdx.x * RED_VPC + k * 256 + tid;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[k][i] = 0.f;
+  }
+  for (int r = 0; r < p.world; ++r) {          // fixed order 0..world-1
+    uint4 v[RED_U];
+#pragma unroll
+    for (int k = 0; k < RED_U; ++k) {
+      v[k] = make_uint4(0, 0, 0, 0);
+      if (vi[k] < len) v[k] = (r == p.rank) ? own[vi[k]] : __ldcg(stg + static_cast<size_t>(r) * per + vi[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < RED_U; ++k) acc8<kBF16>(a[k], v[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < RED_U; ++k) {
+    if (vi[k] >= len) continue;
+    uint4 o;
+    o.x = Elem<kBF16>::pack(a[k][0] * p.scale, a[k][1] * p.scale);
+    o.y = Elem<kBF16>::pack(a[k][2] * p.scale, a[k][3] * p.scale);
+    o.z = Elem<kBF16>::pack(a[k][4] * p.scale, a[k][5] * p.scale);
+    o.w = Elem<kBF16>::pack(a[k][6] * p.scale, a[k][7] * p.scale);
+    own[vi[k]] = o;
+  }
+}
+
 static PFN_cuMemGetAddressRange_v3020 get_addr_range() {
   static PFN_cuMemGetAddressRange_v3020 fn = nullptr;
   if (fn == nullptr) {
@@ -405,7 +474,45 @@ int ub200_peer_allreduce(const ub200_peer_allreduce_args* a, ub200_stream_t stre
   p.scale = a->scale;
   p.timeout_cycles = a->timeout_ms > 0 ? static_cast<long long>(a->timeout_ms) * 1900000ll : 38000000000ll;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (a->max_ctas <= 0) {
+  if (a->max_ctas < 0) {
+    // form 3: copy engines for the NVLink transfers, SMs for the flags and the local reduction
+    const long long v_lo = p.rank * per;
+    long long len = p.nvec - v_lo;
+    if (len > per) len = per;
+    if (len < 0) len = 0;
+    for (int j = 0; j + 1 < a->world; ++j) {
+      const int q = (p.rank + 1 + j) % a->world;
+      long long q_len = p.nvec - static_cast<long long>(q) * per;
+      if (q_len > per) q_len = per;
+      if (q_len > 0)
+        UB_CHECK_CUDA(cudaMemcpyAsync(p.stage[q] + static_cast<size_t>(p.rank) * per * 16,
+                                      p.buf[p.rank] + p.byte_offset + static_cast<size_t>(q) * per * 16,
+                                      static_cast<size_t>(q_len) * 16, cudaMemcpyDeviceToDevice, s));
+    }
+    {
+      ub::ProfScope prof(s);
+      ub::peer_sync_kernel<1><<<1, 32, 0, s>>>(p);
+    }
+    if (len > 0) {
+      const unsigned gc = static_cast<unsigned>((len + ub::RED_VPC - 1) / ub::RED_VPC);
+      ub::ProfScope prof(s);
+      if (a->dtype == UB200_BF16) ub::peer_reduce_local_kernel<true><<<gc, 256, 0, s>>>(p);
+      else ub::peer_reduce_local_kernel<false><<<gc, 256, 0, s>>>(p);
+      for (int j = 0; j + 1 < a->world; ++j) {
+        const int q = (p.rank + 1 + j) % a->world;
+        UB_CHECK_CUDA(cudaMemcpyAsync(p.buf[q] + p.byte_offset + static_cast<size_t>(v_lo) * 16,
+                                      p.buf[p.rank] + p.byte_offset + static_cast<size_t>(v_lo) * 16,
+                                      static_cast<size_t>(len) * 16, cudaMemcpyDeviceToDevice, s));
+      }
+    }
+    {
+      ub::ProfScope prof(s);
+      ub::peer_sync_kernel<2><<<1, 32, 0, s>>>(p);
+    }
+    UB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (a->max_ctas == 0) {
     // form 2: work-sized grids of short-lived CTAs (push kernel, then reduce kernel)
     if (a->world > 1) {
       ub::ProfScope prof(s);

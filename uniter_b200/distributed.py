@@ -113,10 +113,11 @@ class PeerExchange(object):
         a.timeout_ms = self.timeout_ms
         return a
 
-    def all_reduce(self, lo, hi, max_ctas=0):
+    def all_reduce(self, lo, hi, max_ctas=-1):
         """flat[lo:hi] <- mean over ranks, in place, on the current stream (lo, hi multiples of 8).
-        max_ctas 0: a push kernel + a reduce kernel of short-lived CTAs sized by the work (the form that
-        yields SMs to the backward it overlaps); > 0: one persistent kernel of that many CTAs."""
+        max_ctas < 0 (default): the copy engines move the bytes over NVLink (memcpy nodes), the SMs only
+        run the flag barriers and the local reduction — nothing competes with the backward it overlaps;
+        0: a push kernel + a reduce kernel of short-lived CTAs; > 0: one persistent kernel of that many CTAs."""
         from . import _lib
         key = (lo, hi, max_ctas)
         a = self._args.get(key)
@@ -152,8 +153,8 @@ def broadcast_parameters(model, root=0):
 class GradientReducer:
     """Average gradients over ranks: in-place all-reduce of slices of the model's gradient arena."""
 
-    def __init__(self, model, overlap_chunks=4, sm_reserve=0, transport="nccl", peer_ctas=0,
-                 peer_tail_ctas=0):
+    def __init__(self, model, overlap_chunks=4, sm_reserve=0, transport="nccl", peer_ctas=-1,
+                 peer_tail_ctas=-1):
         """`overlap_chunks` > 1: the encoder layers are all-reduced in that many groups (top group
         first, together with the task-head / pooler slice, which is final by then) while the backward
         of the earlier layers still runs; only the embedding front-end slice is reduced after the
@@ -162,9 +163,9 @@ class GradientReducer:
         same number of CTAs (must be called by all ranks).  Measured on 2 x B200 (C2,
         profiles/r01_scale2_variants.json): reserving SMs cost more than it saved, hence default 0.
         `transport` "peer": the slices are exchanged by the library's own NVLink peer-memory kernel
-        (PeerExchange; `peer_ctas` / `peer_tail_ctas`: 0 = work-sized grids of short-lived CTAs, > 0 =
-        one persistent kernel of that many CTAs, for the slices shipped while the backward runs / after
-        it) instead of NCCL — no host involvement, so the whole step including the
+        (PeerExchange; `peer_ctas` / `peer_tail_ctas` select its form for the slices shipped while the
+        backward runs / after it: < 0 copy engines + local reduction, 0 short-lived CTAs, > 0 one persistent
+        kernel of that many CTAs) instead of NCCL — no host involvement, so the whole step including the
         exchange is one CUDA graph."""
         self.model = model
         self.arena = GradArena.attach(model)
