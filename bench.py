@@ -946,7 +946,7 @@ def main():
         T = sum(sum(host[i]["lens"]) for i in range(nt)) / nt
         gemm_flops = 3.0 * NL * 24.0 * ARCH["H"] ** 2 * T          # dense-projection part of §8d
         traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if os.path.exists(tp):                                      # from the committed ncu capture
             with open(tp) as fh:
                 tj = json.load(fh)

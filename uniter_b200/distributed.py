@@ -300,6 +300,17 @@ class GradientReducer:
             if w is not None:
                 w.wait()
 
+    def reset_step_state(self):
+        """Forget what this step has shipped / how many forwards each encoder ran since the last reduce().
+        GraphedStep calls it before capturing a step: its warm-up steps run without the reducer (a capture
+        must not communicate), so the per-step counters that reduce() normally clears are stale."""
+        self._pending = []
+        self._done = []
+        self._bwd_seen = {}
+        self._tail = False
+        for enc in self.encoders:
+            enc._fwd_since_reduce = 0
+
     def backward_and_reduce(self, loss):
         """loss.backward() with the gradients all-reduced slice by slice while the rest of the
         backward is still running (replaces the non-overlapped Horovod call of

@@ -158,6 +158,8 @@ class GraphedStep(object):
         torch.cuda.current_stream().wait_stream(s)
         self.optimizer = opt
         self.reducer = red
+        if red is not None:
+            red.reset_step_state()        # the warm-up forwards were not followed by a reduce()
         if opt is not None:
             opt.prepare()
         if self.pool is None:
