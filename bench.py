@@ -62,10 +62,11 @@ def parse():
                     help="N>1: SMs left to the overlapped all-reduce (and its CTA cap)")
     ap.add_argument("--no-graph", action="store_true",
                     help="enqueue every step from Python (eager) instead of replaying CUDA graphs")
-    ap.add_argument("--allreduce", default="after", choices=["after", "split", "in-graph", "peer"],
-                    help="N>1 graph mode: 'peer' = the gradient slices are exchanged by the library's own NVLink "
-                         "peer-memory kernel (csrc/peer.cu) as nodes of the step's ONE graph, overlapped with the "
-                         "backward (falls back to 'after' if the start-up self-test of the exchange fails); "
+    ap.add_argument("--allreduce", default="peer", choices=["after", "split", "in-graph", "peer"],
+                    help="N>1: 'peer' (default) = the gradient slices are exchanged over NVLink peer memory by the "
+                         "library itself (csrc/peer.cu: copy-engine transfers + flag / local-reduction kernels) as nodes "
+                         "of the step's ONE graph, overlapped with the backward; falls back to 'after' if the start-up "
+                         "self-test fails or a flag wait expires; "
                          "'after' = NCCL all-reduce of the arena after each replay; 'split' = the step is "
                          "captured as one graph per layer group and each group's slice is all-reduced (eagerly, on a "
                          "side stream) while the next group's graph runs; 'in-graph' = NCCL captured inside the graph "
