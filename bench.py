@@ -70,7 +70,7 @@ def parse():
                          "'after' = NCCL all-reduce of the arena after each replay; 'split' = the step is "
                          "captured as one graph per layer group and each group's slice is all-reduced (eagerly, on a "
                          "side stream) while the next group's graph runs; 'in-graph' = NCCL captured inside the graph "
-                         "(hangs with this torch / NCCL build: measured, kept for experiments only)")
+                         "(split / in-graph: experimental, not re-measured since captures became local events)")
     ap.add_argument("--peer-ctas", type=int, default=-1,
                     help="--allreduce peer: form of the exchange that overlaps the backward: -1 = copy engines move the "
                          "bytes, SMs only reduce locally; 0 = push + reduce kernels of short-lived CTAs; N > 0 = one "
@@ -756,9 +756,9 @@ def main():
             return model(batch, "itm")[0].mean()
         raise ValueError(task)
 
-    # N > 1: the gradient all-reduces are captured INSIDE the graph (overlapped with the backward on a
-    # side stream, exactly like the eager reducer); --allreduce after keeps them out of the graph and
-    # issues them after each replay (fallback; chosen automatically if the in-graph capture fails)
+    # N > 1: the gradient exchange is captured INSIDE the graph (peer transport: memcpy + kernel nodes on a
+    # side stream, overlapped with the backward); --allreduce after keeps it out of the graph and issues
+    # NCCL all-reduces after each replay (the fallback if the peer self-test fails or a flag wait expires)
     ar_mode = "none" if reducer is None else args.allreduce
     graphed = None
     if not args.no_graph:

@@ -52,8 +52,11 @@ class GraphedStep(object):
         top layer group, after every further layer group, after the embedding backward); on replay each
         slice's NCCL all-reduce is issued eagerly on the reducer's side stream right after its graph and
         overlaps the next graph; the tail graph (never-touched gradients zeroed, optimizer) runs after
-        the last all-reduce.  "in-graph": NCCL captured inside one graph (hangs with torch 2.11 /
-        NCCL 2.28 in this environment — kept for experiments).
+        the last all-reduce.  "in-graph": the reducer's exchange is captured inside the ONE graph of the
+        step — what GradientReducer(transport="peer") is built for (its exchange is memcpy + kernel nodes);
+        with the NCCL transport this mode and "split" hung in earlier measurements because capture warm-ups
+        executed collectives the other ranks did not take part in (fixed: captures are local now), and
+        were not re-measured since.
         optimizer: optional FusedAdamW stepped inside the (tail) graph; zero_all_grads: see
         GradArena.begin_step(zero_all=...)."""
         self.module = module
