@@ -75,3 +75,45 @@ def test_broadcast_and_gradient_mean_two_ranks():
         assert torch.equal(red0[n], red1[n]), n
     # every gradient ended up inside ONE flat arena and was reduced there in place (no copy-in/out)
     assert "uniter.encoder.layer.0.attention.self.query.weight" in loc0
+
+
+def test_chunk_shipping_covers_the_arena_exactly_once_and_survives_unreduced_warmups():
+    """Host logic of the overlapped exchange (single process, no collective is issued: the reducer
+    reports the ranges it would ship through its capture callback).  The slices shipped while the
+    backward runs ([head | pooler] + top layer group, then the other groups) plus what reduce() ships
+    afterwards (the front-end) must tile the arena exactly once.  GraphedStep warms a step up WITHOUT the
+    reducer (a capture must not communicate): the per-step counters reduce() normally clears are then
+    stale and nothing may be shipped early until reset_step_state() — the regression that silently
+    removed all overlap (every N = 2 variant at 4.15 ms, profiles/r02_k_*)."""
+    from uniter_b200.heads import UniterForMLM
+    from uniter_b200.model import UniterConfig
+    from uniter_b200 import distributed as ubd
+    cfg = UniterConfig(500, hidden_size=64, num_hidden_layers=4, num_attention_heads=1,
+                       intermediate_size=128, max_position_embeddings=32)
+    model = UniterForMLM(cfg, 16)
+    red = ubd.GradientReducer(model, overlap_chunks=2)
+    enc = red.encoders[0]
+    shipped = []
+    red._split_cb = lambda ranges, final=False: shipped.append((list(ranges), final))
+
+    def backward_hooks():
+        for lo, hi in ((2, 4), (0, 2)):                    # top chunk first, as _EncoderStack.backward does
+            red._on_chunk(enc, lo, hi)
+
+    enc._fwd_since_reduce = 3                               # two warm-up forwards + the captured one, no reduce()
+    backward_hooks()
+    assert shipped == []                                    # stale counters: everything waits for reduce()
+    red.reset_step_state()
+    enc._fwd_since_reduce = 1                               # the captured step's forward
+    backward_hooks()
+    assert len(shipped) == 2 and not any(f for _, f in shipped)
+    red.reduce()
+    assert shipped[-1][1] is True                           # the remainder, reported as final
+    ranges = sorted(r for rs, _ in shipped for r in rs)
+    pos = 0
+    for lo, hi in ranges:
+        assert lo == pos and hi > lo, (ranges, pos)
+        pos = hi
+    assert pos == red.arena.numel
+    assert all(lo % 8 == 0 and hi % 8 == 0 for lo, hi in ranges)   # 16-byte slices (ub200_peer_allreduce)
+    assert enc._fwd_since_reduce == 0
