@@ -1040,7 +1040,10 @@ def main():
         if world > 1:
             line["gradient_exchange"] = {
                 "mode": ar_mode,
-                "transport": "ub::peer_allreduce_kernel over cudaIpc-mapped NVLink peer memory" if ar_mode == "peer"
+                "transport": ("copy-engine transfers (memcpy nodes) + ub::peer_sync_kernel / ub::peer_reduce_local_kernel "
+                              "over cudaIpc-mapped NVLink peer memory (csrc/peer.cu)" if args.peer_ctas < 0 else
+                              "ub::peer_push_kernel / peer_reduce_kernel / peer_allreduce_kernel over cudaIpc-mapped "
+                              "NVLink peer memory (csrc/peer.cu)") if ar_mode == "peer"
                              else "ncclAllReduce(AVG) on slices of the gradient arena",
                 "bytes_per_rank_per_step": int(GradArena.attach(model).numel) * 2,
                 "note": peer_note}
