@@ -1,4 +1,5 @@
-// Gradient all-reduce over NVLink peer memory: ONE kernel per arena slice, no NCCL, no host.
+// Gradient all-reduce over NVLink peer memory — the library's own exchange: no NCCL and no host on the
+// data path, every piece an ordinary node of the step's CUDA graph.
 //
 // Replaces the Horovod call of the reference's data-parallel path
 // (utils/distributed.py:16-43: flatten -> hvd.allreduce_ (mean) -> unflatten; call sites
@@ -6,26 +7,30 @@
 // (uniter_b200/arena.py); the arenas, one staging buffer and one 256-byte signal block per rank
 // are mapped into every process with cudaIpc (NVSwitch: every peer at full bandwidth).
 //
-// Why not NCCL here.  The exchange has to overlap the backward pass, whose persistent tcgen05 GEMM
-// CTAs own one SM each.  NCCL's kernels (640 threads x ~96 registers) cannot share an SM with a GEMM
-// CTA, so they displace CTAs of the next persistent launch by a whole round; their launch also
-// needs the host (the capture of NCCL inside the step's CUDA graph hangs with this torch / NCCL
-// build).  This kernel is 256 threads x <= 64 registers and no shared memory — 16 K registers, so it
-// co-resides with a GEMM CTA (512 x 80) — and it is an ordinary kernel node of the step's graph.
-//
-// Algorithm (two-shot, push based: only posted stores cross NVLink, so a few CTAs fill the links):
-//   the slice [offset, offset+count) is cut into `world` sub-slices of `per` 16-byte vectors;
-//   A  push   : rank r copies its sub-slice q (q != r) into stage_q[r]              (remote stores)
+// Protocol (two-shot; the slice [offset, offset+count) is cut into `world` sub-slices of `per`
+// 16-byte vectors):
+//   A  push   : rank r copies its sub-slice q (q != r) into stage_q[r]
 //      barrier 1: signal PUSH[r] = epoch on every peer, wait for PUSH[q] >= epoch from all q
 //   C  reduce : rank r sums its own sub-slice r and the world-1 staged copies in fp32 (fixed rank
 //               order -> every rank ends up with bit-identical values), scales (1/world = the
-//               mean Horovod computes) and writes the result into sub-slice r of EVERY arena
+//               mean Horovod computes) and the result goes into sub-slice r of EVERY arena
 //      barrier 2: signal BCAST[r] = epoch on every peer, wait for BCAST[q] >= epoch from all q
-// Epochs are monotonic and live in device memory, so replaying the same captured kernel node is
-// correct.  Hazards: a rank can only enter call e+1 after every peer signalled BCAST of call e,
-// i.e. after every peer has finished reading its staging buffer and this rank's arena.
-// Spin waits are bounded (~20 s): on expiry a sticky error word is set and every later wait of this
-// rank returns at once (wrong data, but never a hung GPU); the host checks the word.
+// Epochs are monotonic and live in device memory, so replaying the same captured nodes is correct.
+// Hazards: a rank can only enter call e+1 after every peer signalled BCAST of call e, i.e. after
+// every peer has finished reading its staging buffer and this rank's arena.  Spin waits are bounded
+// (~20 s): on expiry a sticky error word is set and every later wait of this rank returns at once
+// (wrong data, but never a hung GPU); the host checks the word.
+//
+// Three forms of the same protocol (ub200_peer_allreduce_args.max_ctas), in the order they were built;
+// the measurements that decided between them are in DESIGN.md §6:
+//   > 0  peer_allreduce_kernel: ONE persistent kernel, both phases with SM loads / posted remote stores.
+//        256 threads x <= 64 registers, no shared memory, so a CTA fits next to a persistent GEMM CTA
+//        (512 x 80-96 registers) — but 16 K registers hold only ~32 KB in flight: 148 CTAs reach
+//        590 GB/s (algorithmic, 2 ranks), 32 CTAs 205 GB/s.
+//   = 0  peer_push_kernel + peer_reduce_kernel: work-sized grids of short-lived CTAs.
+//   < 0  (default) the COPY ENGINES move the bytes (cudaMemcpyAsync nodes), peer_sync_kernel runs the
+//        barriers, peer_reduce_local_kernel reduces out of local HBM: nothing competes with the
+//        backward pass the exchange overlaps — the only form that gained from the overlap.
 #include <cudaTypedefs.h>
 #include <string.h>
 
