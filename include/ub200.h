@@ -448,12 +448,17 @@ int ub200_adamw_step(const ub200_adam_segment* segs_dev, const int32_t* blk_star
 /* ------------------------------------------------------------------------------------------
  * Gradient exchange over NVLink peer memory — replaces utils/distributed.py:16-43
  * (all_reduce_and_rescale_tensors: flatten -> hvd.allreduce_ = mean over ranks -> unflatten; call
- * sites train_vqa.py:193-199, pretrain.py:302-308) with ONE kernel per slice of the flat gradient
- * arena: push my copy of sub-slice q to rank q's staging buffer, flag barrier, reduce sub-slice
- * `rank` in fp32 (rank order 0..world-1, so every rank ends up with bit-identical values), write
- * it into every rank's arena, flag barrier.  Only posted stores cross NVLink; the kernel is an
- * ordinary node of the step's CUDA graph (no host, no NCCL) and small enough (256 threads x <= 64
- * registers, no shared memory) to share SMs with the persistent GEMM CTAs of the backward pass it overlaps.
+ * sites train_vqa.py:193-199, pretrain.py:302-308).  One call averages one slice of the flat gradient
+ * arena over the ranks, two-shot: push my copy of sub-slice q to rank q's staging buffer, flag barrier,
+ * reduce sub-slice `rank` in fp32 (rank order 0..world-1, so every rank ends up with bit-identical
+ * values), write it into every rank's arena, flag barrier.  Everything the call enqueues is an
+ * ordinary node of the caller's stream / CUDA graph (no host synchronisation, no NCCL).  `max_ctas`
+ * selects who moves the bytes:
+ *   < 0  the copy engines (cudaMemcpyAsync nodes); 32-thread kernels run the flag barriers and one kernel
+ *        reduces out of local HBM — the form to overlap with compute (it uses no SM for the transfers);
+ *   = 0  a push kernel + a reduce kernel of short-lived CTAs (256 threads) sized by the work;
+ *   > 0  ONE persistent kernel of that many CTAs (256 threads x <= 64 registers, no shared memory:
+ *        a CTA fits next to a persistent GEMM CTA), posted remote stores.
  *
  * Memory (caller-owned, one set per rank, mapped into every process with the ipc calls below):
  *   buf[q]   rank q's arena base (16-bit elements); the slice is [offset, offset + count)
@@ -471,7 +476,7 @@ typedef struct {
   int64_t offset, count;     /* elements; both multiples of 8 (16 bytes) */
   int64_t stage_bytes;       /* size of each staging buffer */
   int32_t dtype;             /* UB200_F16 / UB200_BF16 */
-  int32_t max_ctas;          /* CTAs (256 threads each) the exchange may use (0: 32) */
+  int32_t max_ctas;          /* form of the exchange, see above (< 0: copy engines) */
   float scale;               /* result = scale * sum over ranks; 1/world = Horovod's average */
   int32_t timeout_ms;        /* bound of every flag wait (0: 20 s) */
 } ub200_peer_allreduce_args;
