@@ -42,11 +42,11 @@ def _capped_nccl_group(max_ctas):
 
 class PeerExchange(object):
     """All-reduce (mean) of slices of one flat 16-bit buffer over NVLink peer memory, without NCCL:
-    the kernel of csrc/peer.cu (ub200_peer_allreduce).  Construction is collective: every rank maps
-    every other rank's buffer, staging buffer and signal block with cudaIpc (handles travel through
-    torch.distributed's object all-gather).  `all_reduce(lo, hi)` only enqueues ONE kernel on the
-    current stream — no host synchronisation, capturable in a CUDA graph; every rank must issue the
-    same sequence of calls.  Replaces hvd.allreduce_ of utils/distributed.py:16-43."""
+    ub200_peer_allreduce of csrc/peer.cu.  Construction is collective: every rank maps every other
+    rank's buffer, staging buffer and signal block with cudaIpc (handles travel through
+    torch.distributed's object all-gather).  `all_reduce(lo, hi)` only enqueues a handful of memcpy /
+    kernel nodes on the current stream — no host synchronisation, capturable in a CUDA graph; every
+    rank must issue the same sequence of calls.  Replaces hvd.allreduce_ of utils/distributed.py:16-43."""
 
     def __init__(self, flat, group=None, max_count=None, timeout_ms=0):
         import ctypes as C
